@@ -1,0 +1,1 @@
+from . import fourier_transforms, iso, loss_helpers, projections  # noqa: F401

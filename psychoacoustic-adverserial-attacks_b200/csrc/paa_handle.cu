@@ -1,0 +1,163 @@
+// Handle life cycle of libpaa.so: immutable device tables for one (device, n_fft, hop, sr).
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "paa_fft.cuh"
+#include "paa_internal.h"
+
+namespace {
+
+// torch.hann_window(n, periodic=True) in fp32, step by step as ATen builds it:
+// arange(n+1) * fp32(2*pi/n) -> cos -> * -0.5 -> + 0.5 (first n entries).
+std::vector<float> hann_periodic(int n) {
+    std::vector<float> w(n);
+    const float step = (float)(M_PI * 2.0 / (double)n);
+    for (int i = 0; i < n; ++i) {
+        float a = (float)i * step;
+        w[i] = cosf(a) * -0.5f + 0.5f;
+    }
+    return w;
+}
+
+// Per-lane Stockham twiddles: stage with radix R after Ns points: W_{Ns*R}^{(j mod Ns) * r},
+// j = lane + 32*b, stored [b][r-1][lane] as (cos, -sin) -- the forward sign.
+void stage_twiddles(std::vector<float>& out, int N, int R, int Ns) {
+    const int NB = N / R / 32;
+    for (int b = 0; b < NB; ++b)
+        for (int r = 1; r < R; ++r)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int k = (lane + 32 * b) % Ns;
+                const double th = 2.0 * M_PI * (double)k * (double)r / (double)(Ns * R);
+                out.push_back((float)std::cos(th));
+                out.push_back((float)(-std::sin(th)));
+            }
+}
+
+template <int NFFT>
+void build_tables(std::vector<float>& tw, std::vector<float>& post) {
+    using P = paa::Plan<NFFT>;
+    stage_twiddles(tw, P::N, P::R1, P::R0);
+    stage_twiddles(tw, P::N, P::R2, P::R0 * P::R1);
+    for (int k = 0; k <= P::N / 2; ++k) {
+        const double th = 2.0 * M_PI * (double)k / (double)NFFT;
+        post.push_back((float)std::cos(th));
+        post.push_back((float)std::sin(th));
+    }
+}
+
+size_t round16(size_t b) { return (b + 15) / 16 * 16; }
+
+}  // namespace
+
+extern "C" {
+
+int paa_create(int device, int n_fft, int hop, int sr, paa_handle** out) {
+    if (!out) return PAA_ERR_NULL;
+    *out = nullptr;
+    if (n_fft != 512 && n_fft != 1024) return PAA_ERR_UNSUPPORTED;
+    if (hop <= 0 || sr <= 0) return PAA_ERR_SHAPE;
+    // frames must tile: hop divides n_fft, at least 50 % overlap, float4-aligned frame starts
+    if (n_fft % hop != 0 || n_fft / hop < 2 || hop % 4 != 0 || n_fft / hop > 16) return PAA_ERR_UNSUPPORTED;
+    paa_handle* h = new paa_handle();
+    h->device = device; h->n_fft = n_fft; h->hop = hop; h->sr = sr;
+    h->F = n_fft / 2 + 1; h->R = n_fft / hop;
+    h->bin_hz = (float)(1.0 / ((double)n_fft * (1.0 / (double)sr)));
+    h->h_window = hann_periodic(n_fft);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) {
+        int sms = 0;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (e == cudaSuccess && sms > 0) h->num_sms = sms;
+    }
+    if (e != cudaSuccess) { int rc = paa_cuda_fail(h, e); delete h; return rc; }
+
+    std::vector<float> tw, post;
+    if (n_fft == 1024) build_tables<1024>(tw, post); else build_tables<512>(tw, post);
+    h->off_twiddle = round16((size_t)n_fft * 4);
+    h->off_post = round16(h->off_twiddle + tw.size() * 4);
+    h->blob_bytes = round16(h->off_post + post.size() * 4);
+    std::vector<unsigned char> blob(h->blob_bytes, 0);
+    std::memcpy(blob.data(), h->h_window.data(), (size_t)n_fft * 4);
+    std::memcpy(blob.data() + h->off_twiddle, tw.data(), tw.size() * 4);
+    std::memcpy(blob.data() + h->off_post, post.data(), post.size() * 4);
+    e = cudaMalloc(&h->d_blob, h->blob_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_blob, blob.data(), h->blob_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_thr_tmp, (size_t)h->F * 4);
+    if (e != cudaSuccess) { int rc = paa_cuda_fail(h, e); paa_destroy(h); return rc; }
+    *out = h;
+    return PAA_OK;
+}
+
+int paa_destroy(paa_handle* h) {
+    if (!h) return PAA_OK;
+    cudaFree(h->d_blob);
+    cudaFree(h->d_thr_tmp);
+    cudaFree(h->d_fm_cols);
+    cudaFree(h->d_fm_knots);
+    cudaFree(h->d_fm_inband);
+    delete h;
+    return PAA_OK;
+}
+
+int paa_last_cuda_error(const paa_handle* h) { return h ? h->last_cuda_error : 0; }
+int paa_num_bins(const paa_handle* h) { return h ? h->F : 0; }
+int paa_num_frames(const paa_handle* h, int T) { return (h && T >= 0) ? 1 + T / h->hop : 0; }
+
+size_t paa_scratch_bytes(const paa_handle* h, int rows, int T) {
+    if (!h || rows <= 0 || T <= 0) return 0;
+    return (size_t)kScalarBytes + kPartialBytes + (size_t)rows * (size_t)T * sizeof(float) + 256;
+}
+
+int paa_scalars(const paa_handle* h, const void* scratch, float* out8, void* stream) {
+    if (!h || !scratch || !out8) return PAA_ERR_NULL;
+    PAA_CUDA(h, cudaMemcpyAsync(out8, scratch, PAA_S_COUNT * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PAA_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+    return PAA_OK;
+}
+
+// Pre-interpolate the (phon x freq) penalty grid along frequency for every rfft bin, in fp64,
+// then keep fp32 columns: w(phon_i, f_k) = (1-t) W[i][j] + t W[i][j+1].  Bins whose centre lies
+// outside the grid's frequency range take fill_value (RegularGridInterpolator, bounds_error=False).
+int paa_set_fm_grid(paa_handle* h, const double* phon_knots, int n_phon, const double* freq_knots, int n_freq,
+                    const double* values, double fill_value) {
+    if (!h || !phon_knots || !freq_knots || !values) return PAA_ERR_NULL;
+    if (n_phon < 2 || n_freq < 2 || n_phon > 64) return PAA_ERR_SHAPE;
+    for (int i = 1; i < n_phon; ++i) if (!(phon_knots[i] > phon_knots[i - 1])) return PAA_ERR_SHAPE;
+    for (int j = 1; j < n_freq; ++j) if (!(freq_knots[j] > freq_knots[j - 1])) return PAA_ERR_SHAPE;
+    std::vector<float> cols((size_t)h->F * n_phon), knots(n_phon);
+    std::vector<uint8_t> inband(h->F);
+    for (int k = 0; k < h->F; ++k) {
+        const double f = (double)((float)k * h->bin_hz);         // the reference queries with fp32 bin centres
+        inband[k] = !(f < freq_knots[0] || f > freq_knots[n_freq - 1]);
+        int j = 0;
+        while (j + 1 < n_freq - 1 && freq_knots[j + 1] < f) ++j;   // searchsorted(left) - 1, clipped
+        const double t = (f - freq_knots[j]) / (freq_knots[j + 1] - freq_knots[j]);
+        for (int i = 0; i < n_phon; ++i)
+            cols[(size_t)k * n_phon + i] =
+                inband[k] ? (float)((1.0 - t) * values[i * n_freq + j] + t * values[i * n_freq + j + 1]) : (float)fill_value;
+    }
+    bool uniform = true;
+    const double dk = phon_knots[1] - phon_knots[0];
+    for (int i = 0; i < n_phon; ++i) {
+        knots[i] = (float)phon_knots[i];
+        if (i && std::fabs((phon_knots[i] - phon_knots[i - 1]) - dk) > 1e-12 * std::fabs(dk)) uniform = false;
+    }
+    PAA_CUDA(h, cudaSetDevice(h->device));
+    cudaFree(h->d_fm_cols); cudaFree(h->d_fm_knots); cudaFree(h->d_fm_inband);
+    h->d_fm_cols = nullptr; h->d_fm_knots = nullptr; h->d_fm_inband = nullptr;
+    PAA_CUDA(h, cudaMalloc((void**)&h->d_fm_cols, cols.size() * 4));
+    PAA_CUDA(h, cudaMalloc((void**)&h->d_fm_knots, knots.size() * 4));
+    PAA_CUDA(h, cudaMalloc((void**)&h->d_fm_inband, inband.size()));
+    PAA_CUDA(h, cudaMemcpy(h->d_fm_cols, cols.data(), cols.size() * 4, cudaMemcpyHostToDevice));
+    PAA_CUDA(h, cudaMemcpy(h->d_fm_knots, knots.data(), knots.size() * 4, cudaMemcpyHostToDevice));
+    PAA_CUDA(h, cudaMemcpy(h->d_fm_inband, inband.data(), inband.size(), cudaMemcpyHostToDevice));
+    h->fm_n_phon = n_phon;
+    h->fm_fill = (float)fill_value;
+    h->fm_uniform = uniform ? 1 : 0;
+    h->fm_k0 = knots[0];
+    h->fm_klast = knots[n_phon - 1];
+    h->fm_inv_dk = (float)(1.0 / dk);
+    return PAA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// Internal declarations shared by the translation units of libpaa.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+#include "../../include/paa.h"
+
+#define PAA_VERSION 100
+
+// Host tables of one (n_fft, hop, sr) plan, mirrored on the device.
+struct paa_handle {
+    int device = 0;
+    int n_fft = 0, hop = 0, sr = 0;
+    int F = 0;               // n_fft/2 + 1
+    int R = 0;               // n_fft / hop: frames overlapping one output sample
+    int num_sms = 148;
+    float bin_hz = 0.f;      // fp32(1/(n_fft*(1/sr))): what torch.fft.rfftfreq multiplies arange by
+    mutable int last_cuda_error = 0;
+
+    // one device blob, copied into shared memory by a 1-D TMA bulk copy at kernel start:
+    //   [window n_fft f32][twiddles (per-lane, stages 1..2) float2][post twiddles N/2+1 float2]
+    void* d_blob = nullptr;
+    size_t blob_bytes = 0;
+    size_t off_twiddle = 0, off_post = 0;
+    std::vector<float> h_window;
+
+    // fletcher_munson penalty grid, frequency axis pre-interpolated per rfft bin
+    float* d_fm_cols = nullptr;      // [F][n_phon]  w(phon_knot i, f_k)
+    float* d_fm_knots = nullptr;     // [n_phon]
+    uint8_t* d_fm_inband = nullptr;  // [F] 1 when f_k inside the grid's frequency range
+    int fm_n_phon = 0;
+    float fm_fill = 1.f;
+    int fm_uniform = 0;              // knots equally spaced -> direct cell lookup
+    float fm_k0 = 0.f, fm_klast = 0.f, fm_inv_dk = 0.f;
+    float* d_thr_tmp = nullptr;      // [F] scaled phon threshold for the un-fused spectrum op
+};
+
+// ---- status helpers -------------------------------------------------------------------------
+static inline int paa_cuda_fail(const paa_handle* h, cudaError_t e) {
+    if (h) h->last_cuda_error = (int)e;
+    return PAA_ERR_CUDA;
+}
+#define PAA_CUDA(h, call)                                              \
+    do {                                                               \
+        cudaError_t e__ = (call);                                      \
+        if (e__ != cudaSuccess) return paa_cuda_fail((h), e__);        \
+    } while (0)
+#define PAA_LAUNCH_CHECK(h) PAA_CUDA((h), cudaGetLastError())
+
+// ---- scratch layout (bytes) -----------------------------------------------------------------
+// [0,256)            float scalars[PAA_S_COUNT..]           (PAA_S_* indices)
+// [256, 256+P)       double partials[kMaxBlocks][2]
+// [.., +rows*T*4)    staging buffer for STFT-domain paths (stepped perturbation)
+constexpr int kScalarBytes = 256;
+constexpr int kMaxPartialBlocks = 8192;
+constexpr size_t kPartialBytes = (size_t)kMaxPartialBlocks * 2 * sizeof(double);
+static inline float* scratch_scalars(void* s) { return (float*)s; }
+static inline double* scratch_partials(void* s) { return (double*)((char*)s + kScalarBytes); }
+static inline float* scratch_stage(void* s) { return (float*)((char*)s + kScalarBytes + kPartialBytes); }
+
+// ---- step parameters as the kernels see them -------------------------------------------------
+struct StepDev {
+    const float* grad;
+    float* m;
+    float* v;
+    float lr;          // PGD
+    float w1;          // Adam: fp32(1-beta1)  (lerp weight)
+    float beta2;       // Adam
+    float w2;          // Adam: fp32(1-beta2)
+    float neg_step;    // Adam: fp32(-(lr/bias_correction1))
+    float bc2_sqrt;    // Adam: fp32(sqrt(bias_correction2))
+    float eps;         // Adam
+};
+int paa_make_step(const paa_step* step, int* mode, StepDev* out);
+
+// time-domain launches (paa_time.cu)
+int paa_launch_adam_prepass(paa_handle* h, const float* p_in, float* p_out, int64_t n, const StepDev& sd, cudaStream_t st);

@@ -1,0 +1,745 @@
+// STFT-domain half of the hot path for sm_100a (reference: src/training_utils/train.py:38-66,
+// src/core/fourier_transforms.py:4-41, src/core/projections.py:68-159).
+//
+// One kernel template covers every use:
+//   SRC_TIME + SINK_TIME   fused  [PGD step ->] STFT -> per-bin op -> ISTFT -> align   (spectrum never in HBM)
+//   SRC_TIME + SINK_REDUCE [PGD step ->] STFT -> fletcher_munson weighted power, per-block partials
+//   SRC_TIME + SINK_SPEC   compute_stft          SRC_SPEC + SINK_TIME   compute_istft
+//
+// Geometry.  centre=True: frame t covers samples [t*hop - n/2, t*hop + n/2) of the reflect-padded
+// row; output sample n receives the R = n_fft/hop frames t in (n/hop + R/2 - R, n/hop + R/2].
+// A CTA of 8 warps owns S = FT-R+1 consecutive output hop-blocks and transforms the FT = 8*R*Q
+// frames that touch them (R-1 halo frames are recomputed by the neighbour tile).  The input span
+// is staged once in shared memory (float4 loads, reflect at the row ends, PGD step applied on
+// the fly), every warp runs whole frames (paa_fft.cuh), and the inverse frames are overlap-added
+// into a shared accumulator in R phases: frames with equal t mod R never overlap, so plain
+// read-modify-write is race free and the summation order is fixed (deterministic output).
+// Window / twiddle tables arrive by one 1-D TMA bulk copy (cp.async.bulk + mbarrier).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "paa_fft.cuh"
+#include "paa_internal.h"
+
+namespace {
+
+using namespace paa;
+
+constexpr int kWarps = 8;
+constexpr int kThreadsStft = kWarps * 32;
+
+enum { SRC_TIME = 0, SRC_SPEC = 1 };
+enum { SINK_TIME = 0, SINK_SPEC = 1, SINK_REDUCE = 2 };
+enum { OP_NONE = 0, OP_MASK = 1, OP_PHON = 2, OP_SCALE = 3 };
+
+struct StftArgs {
+    // time-domain source [rows, T]
+    const float* x;
+    const float* grad;     // PGD step fused into the tile load when non-null
+    float lr;
+    float* q_out;          // SINK_REDUCE: where the stepped perturbation is stored (nullable)
+    int rows, T, n_frames, hop, R, Q;
+    int frames_per_tile;   // FT
+    int blocks_per_tile;   // S (SINK_TIME) -- owned output hop blocks
+    int tiles_per_row;
+    int vec_ok;            // rows are 16-byte aligned: float4 tile loads allowed
+    // time-domain sink [rows, out_len]
+    float* y;
+    int out_len;
+    // tables
+    const void* blob;
+    unsigned blob_bytes, off_tw, off_post;
+    // per-bin op
+    float bin_hz, f_min, f_max;
+    const float* spl_thresh;
+    float ref_db;
+    const float* scalars;  // OP_SCALE: scalars[PAA_S_SCALE]
+    // spectrum source / sink, element strides in complex numbers
+    const float2* spec_in;
+    float2* spec_out;
+    long long sb, sf, st;
+    // fletcher_munson
+    const float* fm_cols;
+    const float* fm_knots;
+    const unsigned char* fm_inband;
+    int fm_np, fm_uniform;
+    float fm_fill, fm_k0, fm_inv_dk, fm_klast;
+    double* partials;
+};
+
+// ---- TMA 1-D bulk copy + mbarrier (PTX) -----------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    } while (!ok);
+}
+
+// ---- per-bin operators ------------------------------------------------------------------------
+// project_min_max_freqs (projections.py:74-79): keep f < f_min or f > f_max, zero the band between.
+__device__ __forceinline__ void op_mask(const StftArgs& a, int k, float& re, float& im) {
+    const float f = (float)k * a.bin_hz;
+    const float keep = (f < a.f_min || f > a.f_max) ? 1.f : 0.f;
+    re *= keep;
+    im *= keep;
+}
+// project_phon_level (projections.py:142-153): every bin takes the dB round trip
+//   |X| -> 20 log10(|X|+1e-8) -> min(., thr) -> 10^(./20), phase kept.
+__device__ __forceinline__ void op_phon(const float* thr, int k, float& re, float& im) {
+    const float m = sqrtf(fmaf(re, re, im * im));
+    const float db = 20.f * log10f(m + 1e-8f);
+    const float t = thr[k];
+    const float db2 = (db > t) ? t : db;
+    const float mag = exp10f(db2 / 20.f);
+    if (m > 1e-18f) {
+        re = mag * (re / m);
+        im = mag * (im / m);
+    } else {                     // zero / denormal magnitude: the phase comes from atan2 as in torch.angle
+        const float ph = atan2f(im, re);
+        float s, c;
+        sincosf(ph, &s, &c);
+        re = mag * c;
+        im = mag * s;
+    }
+}
+// compute_fm_weighted_norm_interp (projections.py:93-113): P * w(10 log10(P+1e-10), f_k)
+__device__ __forceinline__ float fm_term(const StftArgs& a, int k, float re, float im) {
+    const float m = sqrtf(fmaf(re, re, im * im));
+    const float P = m * m;
+    const float spl = 10.f * log10f(P + 1e-10f);
+    float w = a.fm_fill;
+    if (a.fm_inband[k] && !(spl < a.fm_k0) && !(spl > a.fm_klast)) {
+        int i;
+        if (a.fm_uniform) {
+            i = (int)((spl - a.fm_k0) * a.fm_inv_dk);
+        } else {
+            i = 0;
+            for (int q = 1; q < a.fm_np - 1; ++q) i += (spl > a.fm_knots[q]) ? 1 : 0;
+        }
+        i = max(0, min(i, a.fm_np - 2));
+        const float k0 = a.fm_knots[i], k1 = a.fm_knots[i + 1];
+        const float c0 = __ldg(a.fm_cols + (size_t)k * a.fm_np + i), c1 = __ldg(a.fm_cols + (size_t)k * a.fm_np + i + 1);
+        const float tp = (spl - k0) / (k1 - k0);
+        w = fmaf(tp, c1 - c0, c0);
+    }
+    return P * w;
+}
+
+template <int OP>
+__device__ __forceinline__ void apply_op(const StftArgs& a, const float* thr, float scale, int k, float& re, float& im) {
+    if (OP == OP_MASK) op_mask(a, k, re, im);
+    else if (OP == OP_PHON) op_phon(thr, k, re, im);
+    else if (OP == OP_SCALE) { re *= scale; im *= scale; }
+}
+
+// ---- the spectral middle of one frame -----------------------------------------------------------
+// Works on conjugate-symmetric pairs (k, N-k) of the half-length complex FFT held in `buf`:
+//   forward split  Z -> X[k], X[N-k]   |   op / store / reduce   |   inverse merge  X' -> Z' (scaled by 1/n_fft)
+template <int NFFT, int SRC, int SINK, int OP>
+__device__ __forceinline__ void spectral_middle(const StftArgs& a, float2* buf, const float2* __restrict__ post,
+                                                const float* thr, float scale, int lane, long long spec_off,
+                                                float& acc) {
+    using P = Plan<NFFT>;
+    constexpr int N = P::N;
+    constexpr float inv_n = 1.f / (float)NFFT;
+    auto pair = [&](int k) {
+        const int kn = N - k;                       // partner bin; for k == 0 this is the Nyquist bin N
+        float2 X, Y;                                // X = X[k], Y = X[N-k]
+        if (SRC == SRC_TIME) {
+            const float2 za = buf[P::swz(k)], zb = buf[P::swz(kn & (N - 1))];
+            const float2 w = post[k];               // (cos, sin) of 2 pi k / n_fft
+            const float er = 0.5f * (za.x + zb.x), ei = 0.5f * (za.y - zb.y);
+            const float o_r = 0.5f * (za.y + zb.y), o_i = -0.5f * (za.x - zb.x);
+            const float tr = w.x * o_r + w.y * o_i, ti = w.x * o_i - w.y * o_r;
+            X = make_float2(er + tr, ei + ti);
+            Y = make_float2(er - tr, -(ei - ti));
+        } else {
+            X = a.spec_in[spec_off + (long long)k * a.sf];
+            Y = a.spec_in[spec_off + (long long)kn * a.sf];
+        }
+        if (SINK == SINK_REDUCE) {
+            acc += fm_term(a, k, X.x, X.y);
+            if (kn != k) acc += fm_term(a, kn, Y.x, Y.y);
+            return;
+        }
+        apply_op<OP>(a, thr, scale, k, X.x, X.y);
+        if (kn != k) apply_op<OP>(a, thr, scale, kn, Y.x, Y.y);
+        else Y = X;
+        if (SINK == SINK_SPEC) {
+            a.spec_out[spec_off + (long long)k * a.sf] = X;
+            if (kn != k) a.spec_out[spec_off + (long long)kn * a.sf] = Y;
+            return;
+        }
+        // inverse merge; irfft ignores the imaginary parts of the DC and Nyquist bins
+        if (k == 0) { X.y = 0.f; Y.y = 0.f; }
+        const float2 w = post[k];
+        const float ar = X.x + Y.x, ai = X.y - Y.y, br = X.x - Y.x, bi = X.y + Y.y;
+        const float pr = w.x * br - w.y * bi, pi = w.x * bi + w.y * br;
+        buf[P::swz(k)] = make_float2(inv_n * (ar - pi), inv_n * (ai + pr));
+        if (k != 0) buf[P::swz(kn)] = make_float2(inv_n * (ar + pi), inv_n * (pr - ai));
+    };
+#pragma unroll 2
+    for (int i = 0; i < N / 64; ++i) pair(lane + 32 * i);
+    if (lane == 0) pair(N / 2);
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------
+template <int NFFT, int SRC, int SINK, int OP>
+__global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(StftArgs a) {
+    using P = Plan<NFFT>;
+    using L = TwLayout<NFFT>;
+    constexpr int N = P::N;
+    constexpr int F = N + 1;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ float red[kWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hop = a.hop, R = a.R, FT = a.frames_per_tile;
+    const int S = a.blocks_per_tile;
+    const int lin = (FT - 1) * hop + NFFT;                 // staged input span
+
+    // shared-memory carve-up (all offsets multiples of 16 bytes)
+    unsigned char* sp = smem;
+    float* s_win = (float*)sp;
+    const float2* s_tw = (const float2*)(sp + a.off_tw);
+    const float2* s_post = (const float2*)(sp + a.off_post);
+    sp += a.blob_bytes;
+    float* s_thr = (float*)sp;
+    if (OP == OP_PHON) sp += ((F * 4 + 15) / 16) * 16;
+    float2* s_fft = (float2*)sp;
+    sp += (size_t)kWarps * N * sizeof(float2);
+    float* s_in = (float*)sp;
+    if (SRC == SRC_TIME) sp += (size_t)lin * 4;
+    float* s_ola = (float*)sp;
+
+    const int row = blockIdx.x / a.tiles_per_row, ti = blockIdx.x % a.tiles_per_row;
+    // first frame of the tile, and the sample index (unpadded coordinates) of s_in[0]
+    const int t0 = (SINK == SINK_TIME) ? ti * S - R / 2 + 1 : ti * FT;
+    const int in0 = t0 * hop - NFFT / 2;
+
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) tma_bulk_g2s(s_win, a.blob, a.blob_bytes, &bar);
+
+    // ---- stage the input span (reflect padding at the row ends, PGD step fused) ----------------
+    if (SRC == SRC_TIME) {
+        const float* xr = a.x + (size_t)row * a.T;
+        const float* gr = a.grad ? a.grad + (size_t)row * a.T : nullptr;
+        float* qr = (SINK == SINK_REDUCE && a.q_out) ? a.q_out + (size_t)row * a.T : nullptr;
+        const int own_lo = NFFT / 2, own_hi = NFFT / 2 + FT * hop;   // SINK_REDUCE: samples this tile stores to q_out
+        const int T = a.T;
+        for (int i4 = tid; i4 < lin / 4; i4 += kThreadsStft) {
+            const int i = i4 * 4, s = in0 + i;
+            float4 v;
+            if (a.vec_ok && s >= 0 && s + 3 < T) {
+                v = *reinterpret_cast<const float4*>(xr + s);
+                if (gr) {
+                    const float4 g = *reinterpret_cast<const float4*>(gr + s);
+                    v.x += a.lr * ((float)(g.x > 0.f) - (float)(g.x < 0.f));
+                    v.y += a.lr * ((float)(g.y > 0.f) - (float)(g.y < 0.f));
+                    v.z += a.lr * ((float)(g.z > 0.f) - (float)(g.z < 0.f));
+                    v.w += a.lr * ((float)(g.w > 0.f) - (float)(g.w < 0.f));
+                }
+                if (qr && i >= own_lo && i < own_hi) *reinterpret_cast<float4*>(qr + s) = v;
+            } else {
+                float e[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    int sc = s + c;
+                    const bool inside = sc >= 0 && sc < T;
+                    if (sc < 0) sc = -sc;
+                    if (sc >= T) sc = 2 * (T - 1) - sc;
+                    sc = min(max(sc, 0), T - 1);
+                    float val = xr[sc];
+                    if (gr) { const float g = gr[sc]; val += a.lr * ((float)(g > 0.f) - (float)(g < 0.f)); }
+                    if (qr && inside && i + c >= own_lo && i + c < own_hi) qr[sc] = val;
+                    e[c] = val;
+                }
+                v = make_float4(e[0], e[1], e[2], e[3]);
+            }
+            *reinterpret_cast<float4*>(s_in + i) = v;
+        }
+    }
+    if (SINK == SINK_TIME)
+        for (int i4 = tid; i4 < S * hop / 4; i4 += kThreadsStft) *reinterpret_cast<float4*>(s_ola + i4 * 4) = make_float4(0, 0, 0, 0);
+
+    // ---- max_phon: scaled threshold  thr[k] = spl_thresh[k] - max(spl_thresh) + reference_db ------
+    float scale = 1.f;
+    if (OP == OP_SCALE) scale = a.scalars[PAA_S_SCALE];
+    if (OP == OP_PHON) {
+        float mx = -INFINITY;
+        for (int k = tid; k < F; k += kThreadsStft) mx = fmaxf(mx, a.spl_thresh[k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) red[warp] = mx;
+        __syncthreads();
+        mx = red[0];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) mx = fmaxf(mx, red[w]);
+        for (int k = tid; k < F; k += kThreadsStft) s_thr[k] = (a.spl_thresh[k] - mx) + a.ref_db;
+    }
+    mbar_wait(&bar, 0);
+    __syncthreads();
+
+    // ---- frames ----------------------------------------------------------------------------------
+    float2* buf = s_fft + (size_t)warp * N;
+    const float2* win2 = reinterpret_cast<const float2*>(s_win);
+    float acc = 0.f;
+    for (int r = 0; r < R; ++r) {
+        for (int q = 0; q < a.Q; ++q) {
+            const int f = (warp * a.Q + q) * R + r;
+            const int t = t0 + f;
+            if (t < 0 || t >= a.n_frames) continue;              // warp-uniform
+            const long long spec_off = (long long)row * a.sb + (long long)t * a.st;
+            if (SRC == SRC_TIME) {
+                const float2* x2 = reinterpret_cast<const float2*>(s_in + f * hop);
+                fft_warp<NFFT, -1>(
+                    buf, s_tw, lane,
+                    [&](int m) { const float2 xv = x2[m], wv = win2[m]; return make_float2(xv.x * wv.x, xv.y * wv.y); },
+                    [&](int m, float2 v) { buf[P::swz(m)] = v; });
+                __syncwarp();
+            }
+            spectral_middle<NFFT, SRC, SINK, OP>(a, buf, s_post, s_thr, scale, lane, spec_off, acc);
+            if (SINK == SINK_TIME) {
+                __syncwarp();
+                const int obase = (f - R + 1) * hop;                 // owned-region coordinate of frame sample 0
+                const int olim = S * hop;
+                fft_warp<NFFT, +1>(
+                    buf, s_tw, lane, [&](int m) { return buf[P::swz(m)]; },
+                    [&](int m, float2 v) {
+                        const int o = obase + 2 * m;
+                        if (o >= 0 && o < olim) {
+                            const float2 wv = win2[m];
+                            float2* dst = reinterpret_cast<float2*>(s_ola + o);
+                            float2 cur = *dst;
+                            cur.x += v.x * wv.x;
+                            cur.y += v.y * wv.y;
+                            *dst = cur;
+                        }
+                    });
+            }
+        }
+        if (SINK == SINK_TIME) __syncthreads();                  // next phase overlaps these frames
+    }
+
+    // ---- epilogue -----------------------------------------------------------------------------------
+    if (SINK == SINK_TIME) {
+        // y[n] = ola[n] / sum_t w^2[n + n/2 - t*hop]  (torch.istft's window envelope), zero past hop*(T'-1)
+        float* yr = a.y + (size_t)row * a.out_len;
+        const int n_lo = ti * S * hop;
+        const int valid = hop * (a.n_frames - 1);
+        for (int o = tid; o < S * hop; o += kThreadsStft) {
+            const int n = n_lo + o;
+            if (n >= a.out_len) break;
+            float out = 0.f;
+            if (n < valid) {
+                const int u = n + NFFT / 2, ub = u / hop, qq = u - ub * hop;
+                float env = 0.f;
+                for (int d = R - 1; d >= 0; --d) {
+                    const int t = ub - d;
+                    if (t >= 0 && t < a.n_frames) { const float wv = s_win[d * hop + qq]; env += wv * wv; }
+                }
+                out = s_ola[o] / env;
+            }
+            yr[n] = out;
+        }
+    } else if (SINK == SINK_REDUCE) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < kWarps; ++w) s += (double)red[w];
+            a.partials[2 * (size_t)blockIdx.x] = s;
+            a.partials[2 * (size_t)blockIdx.x + 1] = 0.0;
+        }
+    }
+}
+
+// ---- fletcher_munson finalize: norm = sqrt(sum), scale = norm <= eps ? 1 : eps / max(norm, 1e-8) ---
+__global__ void k_fm_finalize(const double* partials, int nblocks, float* scalars, float fm_eps, int apply) {
+    __shared__ double sh[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) s += partials[2 * i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sh[w];
+        const float norm = sqrtf((float)tot);
+        float scale = 1.f;
+        if (apply && !(norm <= fm_eps)) scale = __frcp_rn(fmaxf(norm, 1e-8f)) * fm_eps;   // projections.py:130-132
+        scalars[PAA_S_SCALE] = scale;
+        scalars[PAA_S_NORM] = norm;
+        scalars[PAA_S_AUX0] = (float)tot;
+        scalars[PAA_S_AUX1] = 0.f;
+    }
+}
+
+// p_out[row, n] = scale * q[row, n] for n < valid, 0 up to out_len:  ISTFT(s * STFT(q)) = s * q on the
+// samples the inverse reconstructs (used when the caller waives the exact round trip).
+__global__ void k_fm_scale_identity(const float* __restrict__ q, float* __restrict__ out, int rows, int T, int out_len,
+                                    int valid, const float* __restrict__ scalars) {
+    const float sc = scalars[PAA_S_SCALE];
+    const long long n = (long long)rows * out_len;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / out_len), c = (int)(i - (long long)r * out_len);
+        out[i] = (c < valid && c < T) ? q[(size_t)r * T + c] * sc : 0.f;
+    }
+}
+
+// ---- element-wise spectrum kernels for the un-fused public functions -------------------------------
+template <int OP>
+__global__ void k_spec_op(StftArgs a, int F, const float* thr_scaled) {
+    const long long n = (long long)a.rows * F * a.n_frames;
+    const float scale = OP == OP_SCALE ? a.scalars[PAA_S_SCALE] : 1.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        // enumerate in the order of the smallest stride for coalescing
+        int b, k, t;
+        if (a.sf <= a.st) { k = (int)(i % F); t = (int)((i / F) % a.n_frames); b = (int)(i / ((long long)F * a.n_frames)); }
+        else { t = (int)(i % a.n_frames); k = (int)((i / a.n_frames) % F); b = (int)(i / ((long long)F * a.n_frames)); }
+        const long long off = b * a.sb + k * a.sf + t * a.st;
+        float2 X = a.spec_in[off];
+        apply_op<OP>(a, thr_scaled, scale, k, X.x, X.y);
+        a.spec_out[off] = X;
+    }
+}
+__global__ void k_thr_scaled(const float* spl, int F, float ref_db, float* out) {
+    __shared__ float sh[32];
+    float mx = -INFINITY;
+    for (int k = threadIdx.x; k < F; k += blockDim.x) mx = fmaxf(mx, spl[k]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = sh[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, sh[w]);
+    for (int k = threadIdx.x; k < F; k += blockDim.x) out[k] = (spl[k] - mx) + ref_db;
+}
+__global__ void k_spec_fm_partials(StftArgs a, int F) {
+    const long long n = (long long)a.rows * F * a.n_frames;
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int b, k, t;
+        if (a.sf <= a.st) { k = (int)(i % F); t = (int)((i / F) % a.n_frames); b = (int)(i / ((long long)F * a.n_frames)); }
+        else { t = (int)(i % a.n_frames); k = (int)((i / a.n_frames) % F); b = (int)(i / ((long long)F * a.n_frames)); }
+        const float2 X = a.spec_in[b * a.sb + k * a.sf + t * a.st];
+        acc += fm_term(a, k, X.x, X.y);
+    }
+    __shared__ float sh[32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += (double)sh[w];
+        a.partials[2 * (size_t)blockIdx.x] = s;
+        a.partials[2 * (size_t)blockIdx.x + 1] = 0.0;
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+template <int NFFT>
+size_t smem_bytes(const paa_handle* h, int src, int sink, int op, int FT, int S) {
+    constexpr int N = NFFT / 2;
+    size_t b = h->blob_bytes;
+    if (op == OP_PHON) b += (((N + 1) * 4 + 15) / 16) * 16;
+    b += (size_t)kWarps * N * sizeof(float2);
+    if (src == SRC_TIME) b += (size_t)((FT - 1) * h->hop + NFFT) * 4;
+    if (sink == SINK_TIME) b += (size_t)S * h->hop * 4;
+    return b;
+}
+
+template <int NFFT, int SRC, int SINK, int OP>
+int launch(paa_handle* h, StftArgs& a, int grid, cudaStream_t st) {
+    size_t smem = smem_bytes<NFFT>(h, SRC, SINK, OP, a.frames_per_tile, a.blocks_per_tile);
+    auto kern = k_stft<NFFT, SRC, SINK, OP>;
+    static bool configured = false;       // per instantiation; the attribute is idempotent
+    if (!configured) {
+        PAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    kern<<<grid, kThreadsStft, smem, st>>>(a);
+    PAA_LAUNCH_CHECK(h);
+    return PAA_OK;
+}
+
+template <int SRC, int SINK, int OP>
+int launch_n(paa_handle* h, StftArgs& a, int grid, cudaStream_t st) {
+    if (h->n_fft == 1024) return launch<1024, SRC, SINK, OP>(h, a, grid, st);
+    return launch<512, SRC, SINK, OP>(h, a, grid, st);
+}
+
+void fill_common(const paa_handle* h, StftArgs& a, int rows, int T, int n_frames) {
+    a.rows = rows; a.T = T; a.n_frames = n_frames; a.hop = h->hop; a.R = h->R;
+    a.Q = h->R >= 4 ? 1 : 2;
+    a.frames_per_tile = kWarps * a.R * a.Q;
+    a.blocks_per_tile = a.frames_per_tile - a.R + 1;
+    a.blob = h->d_blob; a.blob_bytes = (unsigned)h->blob_bytes;
+    a.off_tw = (unsigned)h->off_twiddle; a.off_post = (unsigned)h->off_post;
+    a.bin_hz = h->bin_hz;
+    a.fm_cols = h->d_fm_cols; a.fm_knots = h->d_fm_knots; a.fm_inband = h->d_fm_inband;
+    a.fm_np = h->fm_n_phon; a.fm_uniform = h->fm_uniform; a.fm_fill = h->fm_fill;
+    a.fm_k0 = h->fm_k0; a.fm_klast = h->fm_klast; a.fm_inv_dk = h->fm_inv_dk;
+}
+
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+// torch.istft refuses windows whose overlap-add envelope (after trimming n_fft/2) falls below 1e-11
+bool nola_ok(const paa_handle* h, int n_frames) {
+    const int n = h->n_fft, hop = h->hop;
+    const long long valid = (long long)hop * (n_frames - 1);
+    auto env_at = [&](long long pos) {
+        const long long u = pos + n / 2, ub = u / hop;
+        const int q = (int)(u - ub * hop);
+        float e = 0.f;
+        for (int d = h->R - 1; d >= 0; --d) {
+            long long t = ub - d;
+            if (t >= 0 && t < n_frames) { float w = h->h_window[d * hop + q]; e += w * w; }
+        }
+        return e;
+    };
+    const long long edge = std::min<long long>(valid, 2LL * n);
+    for (long long p = 0; p < edge; ++p)
+        if (std::fabs(env_at(p)) < 1e-11f) return false;
+    for (long long p = std::max<long long>(edge, valid - 2LL * n); p < valid; ++p)
+        if (std::fabs(env_at(p)) < 1e-11f) return false;
+    return true;
+}
+
+int check_time_shape(const paa_handle* h, int rows, int T) {
+    if (rows <= 0 || T <= 0) return PAA_ERR_SHAPE;
+    if (T <= h->n_fft / 2) return PAA_ERR_SHAPE;       // reflect padding needs n_fft/2 < T (torch raises too)
+    return PAA_OK;
+}
+
+// The fused path shared by min_max_freqs / max_phon / fletcher_munson pass B.
+template <int OP>
+int run_fused(paa_handle* h, StftArgs& a, const float* src, const float* grad, float lr, float* p_out, int rows, int T,
+              int out_len, cudaStream_t st) {
+    const int n_frames = 1 + T / h->hop;
+    fill_common(h, a, rows, T, n_frames);
+    if (!nola_ok(h, n_frames)) return PAA_ERR_NOLA;
+    a.x = src; a.grad = grad; a.lr = lr; a.y = p_out; a.out_len = out_len;
+    a.vec_ok = aligned16(src) && (T % 4 == 0) && (!grad || aligned16(grad));
+    const int out_blocks = (out_len + h->hop - 1) / h->hop;
+    a.tiles_per_row = std::max(1, (out_blocks + a.blocks_per_tile - 1) / a.blocks_per_tile);
+    return launch_n<SRC_TIME, SINK_TIME, OP>(h, a, rows * a.tiles_per_row, st);
+}
+
+// Adam cannot be folded into the tile load (halo samples would be updated twice), so it runs as a
+// streaming pre-pass into the scratch staging buffer; PGD is fused.
+int prepare_source(paa_handle* h, const float* p_in, int rows, int T, const paa_step* step, void* scratch,
+                   cudaStream_t st, const float** src, const float** grad, float* lr) {
+    int mode = 0;
+    StepDev sd{};
+    int rc = paa_make_step(step, &mode, &sd);
+    if (rc) return rc;
+    *src = p_in; *grad = nullptr; *lr = 0.f;
+    if (mode == PAA_STEP_PGD) { *grad = sd.grad; *lr = sd.lr; }
+    else if (mode == PAA_STEP_ADAM) {
+        if (!scratch) return PAA_ERR_NULL;
+        float* stage = scratch_stage(scratch);
+        rc = paa_launch_adam_prepass(h, p_in, stage, (int64_t)rows * T, sd, st);
+        if (rc) return rc;
+        *src = stage;
+    }
+    return PAA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int paa_project_min_max_freqs(paa_handle* h, const float* p_in, float* p_out, int rows, int T, int out_len,
+                              double min_freq, double max_freq, const paa_step* step, void* scratch, void* stream) {
+    if (!h || !p_in || !p_out) return PAA_ERR_NULL;
+    int rc = check_time_shape(h, rows, T);
+    if (rc) return rc;
+    if (out_len <= 0) return PAA_ERR_SHAPE;
+    if (p_in == p_out) return PAA_ERR_ALIAS;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float *src, *grad; float lr;
+    rc = prepare_source(h, p_in, rows, T, step, scratch, st, &src, &grad, &lr);
+    if (rc) return rc;
+    StftArgs a{};
+    a.f_min = (float)min_freq; a.f_max = (float)max_freq;
+    return run_fused<OP_MASK>(h, a, src, grad, lr, p_out, rows, T, out_len, st);
+}
+
+int paa_project_max_phon(paa_handle* h, const float* p_in, float* p_out, int rows, int T, int out_len,
+                         const float* spl_thresh_F, double phon_reference_db, const paa_step* step, void* scratch,
+                         void* stream) {
+    if (!h || !p_in || !p_out || !spl_thresh_F) return PAA_ERR_NULL;
+    int rc = check_time_shape(h, rows, T);
+    if (rc) return rc;
+    if (out_len <= 0) return PAA_ERR_SHAPE;
+    if (p_in == p_out) return PAA_ERR_ALIAS;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float *src, *grad; float lr;
+    rc = prepare_source(h, p_in, rows, T, step, scratch, st, &src, &grad, &lr);
+    if (rc) return rc;
+    StftArgs a{};
+    a.spl_thresh = spl_thresh_F; a.ref_db = (float)phon_reference_db;
+    return run_fused<OP_PHON>(h, a, src, grad, lr, p_out, rows, T, out_len, st);
+}
+
+int paa_project_fletcher_munson(paa_handle* h, const float* p_in, float* p_out, int rows, int T, int out_len,
+                                double fm_epsilon, int exact_roundtrip, const paa_step* step, void* scratch,
+                                void* stream) {
+    if (!h || !p_in || !p_out || !scratch) return PAA_ERR_NULL;
+    if (!h->d_fm_cols) return PAA_ERR_STATE;
+    int rc = check_time_shape(h, rows, T);
+    if (rc) return rc;
+    if (out_len <= 0) return PAA_ERR_SHAPE;
+    if (p_in == p_out) return PAA_ERR_ALIAS;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float *src, *grad; float lr;
+    rc = prepare_source(h, p_in, rows, T, step, scratch, st, &src, &grad, &lr);
+    if (rc) return rc;
+    // pass A: [PGD step ->] STFT -> weighted power partials; the stepped signal goes to the staging buffer
+    const int n_frames = 1 + T / h->hop;
+    if (!nola_ok(h, n_frames)) return PAA_ERR_NOLA;
+    StftArgs a{};
+    fill_common(h, a, rows, T, n_frames);
+    a.x = src; a.grad = grad; a.lr = lr;
+    a.q_out = grad ? scratch_stage(scratch) : nullptr;
+    a.vec_ok = aligned16(src) && (T % 4 == 0) && (!grad || aligned16(grad));
+    a.tiles_per_row = (n_frames + a.frames_per_tile - 1) / a.frames_per_tile;
+    a.partials = scratch_partials(scratch);
+    const int grid = rows * a.tiles_per_row;
+    if (grid > kMaxPartialBlocks) return PAA_ERR_SHAPE;
+    rc = launch_n<SRC_TIME, SINK_REDUCE, OP_NONE>(h, a, grid, st);
+    if (rc) return rc;
+    float* scalars = scratch_scalars(scratch);
+    k_fm_finalize<<<1, 256, 0, st>>>(a.partials, grid, scalars, (float)fm_epsilon, 1);
+    PAA_LAUNCH_CHECK(h);
+    // pass B: ISTFT(scale * STFT(q)).  q is the stepped signal (staging buffer) or the input itself.
+    const float* q = grad ? scratch_stage(scratch) : src;
+    if (exact_roundtrip) {
+        StftArgs b{};
+        b.scalars = scalars;
+        return run_fused<OP_SCALE>(h, b, q, nullptr, 0.f, p_out, rows, T, out_len, st);
+    }
+    const long long n = (long long)rows * out_len;
+    const int g2 = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8);
+    k_fm_scale_identity<<<std::max(g2, 1), 256, 0, st>>>(q, p_out, rows, T, out_len, h->hop * (n_frames - 1), scalars);
+    PAA_LAUNCH_CHECK(h);
+    return PAA_OK;
+}
+
+int paa_stft(paa_handle* h, const float* x, int rows, int T, float* spec, int64_t sb, int64_t sf, int64_t stt,
+             void* stream) {
+    if (!h || !x || !spec) return PAA_ERR_NULL;
+    int rc = check_time_shape(h, rows, T);
+    if (rc) return rc;
+    const int n_frames = 1 + T / h->hop;
+    StftArgs a{};
+    fill_common(h, a, rows, T, n_frames);
+    a.x = x; a.vec_ok = aligned16(x) && (T % 4 == 0);
+    a.spec_out = reinterpret_cast<float2*>(spec); a.sb = sb; a.sf = sf; a.st = stt;
+    a.tiles_per_row = (n_frames + a.frames_per_tile - 1) / a.frames_per_tile;
+    return launch_n<SRC_TIME, SINK_SPEC, OP_NONE>(h, a, rows * a.tiles_per_row, (cudaStream_t)stream);
+}
+
+int paa_istft(paa_handle* h, const float* spec, int64_t sb, int64_t sf, int64_t stt, int rows, int n_frames, float* y,
+              void* stream) {
+    if (!h || !spec || !y) return PAA_ERR_NULL;
+    if (rows <= 0 || n_frames < 2) return PAA_ERR_SHAPE;
+    if (!nola_ok(h, n_frames)) return PAA_ERR_NOLA;
+    StftArgs a{};
+    fill_common(h, a, rows, 0, n_frames);
+    a.spec_in = reinterpret_cast<const float2*>(spec); a.sb = sb; a.sf = sf; a.st = stt;
+    a.y = y; a.out_len = h->hop * (n_frames - 1);
+    const int out_blocks = n_frames - 1;
+    a.tiles_per_row = std::max(1, (out_blocks + a.blocks_per_tile - 1) / a.blocks_per_tile);
+    return launch_n<SRC_SPEC, SINK_TIME, OP_NONE>(h, a, rows * a.tiles_per_row, (cudaStream_t)stream);
+}
+
+static int spec_grid(const paa_handle* h, long long n) {
+    return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8));
+}
+
+int paa_spec_min_max_freqs(paa_handle* h, const float* spec_in, float* spec_out, int rows, int n_frames, int64_t sb,
+                           int64_t sf, int64_t stt, double min_freq, double max_freq, void* stream) {
+    if (!h || !spec_in || !spec_out) return PAA_ERR_NULL;
+    if (rows <= 0 || n_frames <= 0) return PAA_ERR_SHAPE;
+    StftArgs a{};
+    fill_common(h, a, rows, 0, n_frames);
+    a.spec_in = reinterpret_cast<const float2*>(spec_in); a.spec_out = reinterpret_cast<float2*>(spec_out);
+    a.sb = sb; a.sf = sf; a.st = stt; a.f_min = (float)min_freq; a.f_max = (float)max_freq;
+    k_spec_op<OP_MASK><<<spec_grid(h, (long long)rows * h->F * n_frames), 256, 0, (cudaStream_t)stream>>>(a, h->F, nullptr);
+    PAA_LAUNCH_CHECK(h);
+    return PAA_OK;
+}
+
+int paa_spec_phon_level(paa_handle* h, const float* spec_in, float* spec_out, int rows, int n_frames, int64_t sb,
+                        int64_t sf, int64_t stt, const float* spl_thresh_F, double phon_reference_db, void* stream) {
+    if (!h || !spec_in || !spec_out || !spl_thresh_F) return PAA_ERR_NULL;
+    if (rows <= 0 || n_frames <= 0) return PAA_ERR_SHAPE;
+    StftArgs a{};
+    fill_common(h, a, rows, 0, n_frames);
+    a.spec_in = reinterpret_cast<const float2*>(spec_in); a.spec_out = reinterpret_cast<float2*>(spec_out);
+    a.sb = sb; a.sf = sf; a.st = stt;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_thr_scaled<<<1, 256, 0, st>>>(spl_thresh_F, h->F, (float)phon_reference_db, h->d_thr_tmp);
+    PAA_LAUNCH_CHECK(h);
+    k_spec_op<OP_PHON><<<spec_grid(h, (long long)rows * h->F * n_frames), 256, 0, st>>>(a, h->F, h->d_thr_tmp);
+    PAA_LAUNCH_CHECK(h);
+    return PAA_OK;
+}
+
+static int spec_fm(paa_handle* h, const float* spec_in, float* spec_out, int rows, int n_frames, int64_t sb, int64_t sf,
+                   int64_t stt, double fm_epsilon, int apply, void* scratch, cudaStream_t st) {
+    if (!h || !spec_in || !scratch || (apply && !spec_out)) return PAA_ERR_NULL;
+    if (!h->d_fm_cols) return PAA_ERR_STATE;
+    if (rows <= 0 || n_frames <= 0) return PAA_ERR_SHAPE;
+    StftArgs a{};
+    fill_common(h, a, rows, 0, n_frames);
+    a.spec_in = reinterpret_cast<const float2*>(spec_in); a.spec_out = reinterpret_cast<float2*>(spec_out);
+    a.sb = sb; a.sf = sf; a.st = stt;
+    a.partials = scratch_partials(scratch);
+    a.scalars = scratch_scalars(scratch);
+    const long long n = (long long)rows * h->F * n_frames;
+    const int grid = std::min(spec_grid(h, n), kMaxPartialBlocks);
+    k_spec_fm_partials<<<grid, 256, 0, st>>>(a, h->F);
+    PAA_LAUNCH_CHECK(h);
+    k_fm_finalize<<<1, 256, 0, st>>>(a.partials, grid, scratch_scalars(scratch), (float)fm_epsilon, apply);
+    PAA_LAUNCH_CHECK(h);
+    if (apply) {
+        k_spec_op<OP_SCALE><<<spec_grid(h, n), 256, 0, st>>>(a, h->F, nullptr);
+        PAA_LAUNCH_CHECK(h);
+    }
+    return PAA_OK;
+}
+
+int paa_spec_fm_norm(paa_handle* h, const float* spec_in, int rows, int n_frames, int64_t sb, int64_t sf, int64_t stt,
+                     void* scratch, void* stream) {
+    return spec_fm(h, spec_in, nullptr, rows, n_frames, sb, sf, stt, 0.0, 0, scratch, (cudaStream_t)stream);
+}
+
+int paa_spec_fm_project(paa_handle* h, const float* spec_in, float* spec_out, int rows, int n_frames, int64_t sb,
+                        int64_t sf, int64_t stt, double fm_epsilon, void* scratch, void* stream) {
+    return spec_fm(h, spec_in, spec_out, rows, n_frames, sb, sf, stt, fm_epsilon, 1, scratch, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,496 @@
+// Time-domain half of the hot path for sm_100a: the PGD / Adam step on the perturbation fused
+// with the linf / l2 / snr / tv projections (reference: src/training_utils/train.py:155-175,
+// src/core/projections.py:11-66).  Pure HBM streaming: float4 loads, one read of every input,
+// deterministic block -> grid reductions (no float atomics), device-side branch on the norm so
+// the host never synchronises.
+#include <cooperative_groups.h>
+#include <cmath>
+#include "paa_internal.h"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kBlocksPerSm = 8;
+
+enum { NORM_L2 = 0, NORM_SNR = 1, NORM_TV = 2 };
+
+// ---- the optimiser step on one element -----------------------------------------------------
+// PGD  (train.py:161):  p + fp32(lr) * sign(g), sign(0) = sign(nan) = 0.
+// Adam (torch/optim/adam.py:457-547): lerp, mul+addcmul, sqrt/bias2 + eps, addcdiv.
+template <int STEP>
+__device__ __forceinline__ float step_one(float p, float g, float& m, float& v, const StepDev& s) {
+    if (STEP == PAA_STEP_PGD) {
+        float sg = (float)(g > 0.f) - (float)(g < 0.f);
+        return p + s.lr * sg;
+    } else if (STEP == PAA_STEP_ADAM) {
+        m = fmaf(s.w1, g - m, m);
+        v = v * s.beta2;
+        v = v + (s.w2 * g) * g;
+        float denom = sqrtf(v) / s.bc2_sqrt + s.eps;
+        return p + (s.neg_step * m) / denom;
+    }
+    return p;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// streaming loads for data touched once (clean audio): do not let it displace p in L2
+__device__ __forceinline__ float4 ld4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+
+// Loads 4 elements of p (and grad / Adam state), applies the step, stores the Adam state.
+template <int STEP, bool WRITE_STATE>
+__device__ __forceinline__ float4 stepped4(const float* p, int64_t i, const StepDev& s) {
+    float4 x = ld4(p + i);
+    if (STEP == PAA_STEP_NONE) return x;
+    float4 g = ld4(s.grad + i);
+    float4 m = make_float4(0, 0, 0, 0), v = m;
+    if (STEP == PAA_STEP_ADAM) { m = ld4(s.m + i); v = ld4(s.v + i); }
+    x.x = step_one<STEP>(x.x, g.x, m.x, v.x, s);
+    x.y = step_one<STEP>(x.y, g.y, m.y, v.y, s);
+    x.z = step_one<STEP>(x.z, g.z, m.z, v.z, s);
+    x.w = step_one<STEP>(x.w, g.w, m.w, v.w, s);
+    if (STEP == PAA_STEP_ADAM && WRITE_STATE) { st4(s.m + i, m); st4(s.v + i, v); }
+    return x;
+}
+template <int STEP, bool WRITE_STATE>
+__device__ __forceinline__ float stepped1(const float* p, int64_t i, const StepDev& s) {
+    float x = p[i];
+    if (STEP == PAA_STEP_NONE) return x;
+    float g = s.grad[i], m = 0.f, v = 0.f;
+    if (STEP == PAA_STEP_ADAM) { m = s.m[i]; v = s.v[i]; }
+    x = step_one<STEP>(x, g, m, v, s);
+    if (STEP == PAA_STEP_ADAM && WRITE_STATE) { s.m[i] = m; s.v[i] = v; }
+    return x;
+}
+
+// torch.clamp: NaN stays NaN, bounds applied as min(max(x, lo), hi)
+__device__ __forceinline__ float clamp1(float x, float lo, float hi) {
+    return (x != x) ? x : fminf(fmaxf(x, lo), hi);
+}
+
+// ---- block reduction in double, fixed order -------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int NQ>
+__device__ __forceinline__ void block_sum(double (&acc)[NQ], double* out /* [NQ] or nullptr */) {
+    __shared__ double sh[NQ][kThreads / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        double s = warp_sum(acc[q]);
+        if (lane == 0) sh[q][w] = s;
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            double s = lane < kThreads / 32 ? sh[q][lane] : 0.0;
+            s = warp_sum(s);
+            if (lane == 0 && out) out[q] = s;
+        }
+    }
+}
+
+// ---- kernel: step + clamp (linf), single pass -------------------------------------------------
+template <int STEP, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_step_clamp(const float* p_in, float* p_out,
+                                                        int64_t n, float lo, float hi, bool clamp, StepDev s) {
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x, nth = (int64_t)gridDim.x * kThreads;
+    if (VEC) {
+        const int64_t n4 = n >> 2;
+        for (int64_t i = tid; i < n4; i += nth) {
+            float4 x = stepped4<STEP, true>(p_in, i * 4, s);
+            if (clamp) { x.x = clamp1(x.x, lo, hi); x.y = clamp1(x.y, lo, hi); x.z = clamp1(x.z, lo, hi); x.w = clamp1(x.w, lo, hi); }
+            st4(p_out + i * 4, x);
+        }
+        for (int64_t i = (n4 << 2) + tid; i < n; i += nth) {
+            float x = stepped1<STEP, true>(p_in, i, s);
+            p_out[i] = clamp ? clamp1(x, lo, hi) : x;
+        }
+    } else {
+        for (int64_t i = tid; i < n; i += nth) {
+            float x = stepped1<STEP, true>(p_in, i, s);
+            p_out[i] = clamp ? clamp1(x, lo, hi) : x;
+        }
+    }
+}
+
+// ---- kernel: pass A of l2 / snr / tv ----------------------------------------------------------
+// Reads p (+grad, Adam state) once, writes the stepped perturbation q, and leaves per-block
+// partial sums of   l2: sum q^2      snr: sum q^2, sum clean^2      tv: sum |dq|, sum |dclean|.
+struct ReduceArgs {
+    const float* p_in;
+    float* q_out;        // stepped perturbation (may alias p_in unless NORM_TV with a step)
+    int64_t n;           // rows*T
+    int T;               // row length of p (tv: differences never cross a row end)
+    const float* clean;
+    int64_t clean_n;
+    int clean_T;
+    double* partials;    // [gridDim.x][2]
+    bool write_q;
+};
+
+template <int NORM, int STEP, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_reduce(ReduceArgs a, StepDev s) {
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x, nth = (int64_t)gridDim.x * kThreads;
+    float acc0 = 0.f, acc1 = 0.f;       // per-thread fp32 partials (a few hundred terms), widened below
+    double wide[2] = {0.0, 0.0};
+
+    if (NORM != NORM_TV) {
+        if (VEC) {
+            const int64_t n4 = a.n >> 2;
+            for (int64_t i = tid; i < n4; i += nth) {
+                float4 x = stepped4<STEP, true>(a.p_in, i * 4, s);
+                if (a.write_q) st4(a.q_out + i * 4, x);
+                acc0 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+            }
+            for (int64_t i = (n4 << 2) + tid; i < a.n; i += nth) {
+                float x = stepped1<STEP, true>(a.p_in, i, s);
+                if (a.write_q) a.q_out[i] = x;
+                acc0 += x * x;
+            }
+            if (NORM == NORM_SNR) {
+                const int64_t c4 = a.clean_n >> 2;
+                for (int64_t i = tid; i < c4; i += nth) {
+                    float4 c = ld4_stream(a.clean + i * 4);
+                    acc1 += (c.x * c.x + c.y * c.y) + (c.z * c.z + c.w * c.w);
+                }
+                for (int64_t i = (c4 << 2) + tid; i < a.clean_n; i += nth) { float c = a.clean[i]; acc1 += c * c; }
+            }
+        } else {
+            for (int64_t i = tid; i < a.n; i += nth) {
+                float x = stepped1<STEP, true>(a.p_in, i, s);
+                if (a.write_q) a.q_out[i] = x;
+                acc0 += x * x;
+            }
+            if (NORM == NORM_SNR)
+                for (int64_t i = tid; i < a.clean_n; i += nth) { float c = a.clean[i]; acc1 += c * c; }
+        }
+    } else {
+        // total variation: element i pairs with i+1 unless i is the last sample of its row.
+        // The neighbour's stepped value is recomputed (never read back from q_out), which is
+        // why tv with a fused step needs q_out != p_in.
+        if (VEC) {
+            const int64_t n4 = a.n >> 2;
+            for (int64_t i4 = tid; i4 < n4; i4 += nth) {
+                const int64_t i = i4 * 4;
+                float4 x = stepped4<STEP, false>(a.p_in, i, s);
+                if (a.write_q) st4(a.q_out + i, x);
+                float nx = (i + 4 < a.n) ? stepped1<STEP, false>(a.p_in, i + 4, s) : 0.f;
+                const int c = (int)(i % a.T), Tp = a.T;
+                float t = 0.f;
+                if (c != Tp - 1) t += fabsf(x.y - x.x);
+                if ((c + 1) % Tp != Tp - 1) t += fabsf(x.z - x.y);
+                if ((c + 2) % Tp != Tp - 1) t += fabsf(x.w - x.z);
+                if ((c + 3) % Tp != Tp - 1 && i + 4 < a.n) t += fabsf(nx - x.w);
+                acc0 += t;
+            }
+            for (int64_t i = (n4 << 2) + tid; i < a.n; i += nth) {
+                float x = stepped1<STEP, false>(a.p_in, i, s);
+                if (a.write_q) a.q_out[i] = x;
+                if ((int)(i % a.T) != a.T - 1 && i + 1 < a.n) acc0 += fabsf(stepped1<STEP, false>(a.p_in, i + 1, s) - x);
+            }
+            const int64_t c4 = a.clean_n >> 2;
+            for (int64_t i4 = tid; i4 < c4; i4 += nth) {
+                const int64_t i = i4 * 4;
+                float4 x = ld4(a.clean + i);
+                float nx = (i + 4 < a.clean_n) ? a.clean[i + 4] : 0.f;
+                const int c = (int)(i % a.clean_T), Tc = a.clean_T;
+                float t = 0.f;
+                if (c != Tc - 1) t += fabsf(x.y - x.x);
+                if ((c + 1) % Tc != Tc - 1) t += fabsf(x.z - x.y);
+                if ((c + 2) % Tc != Tc - 1) t += fabsf(x.w - x.z);
+                if ((c + 3) % Tc != Tc - 1 && i + 4 < a.clean_n) t += fabsf(nx - x.w);
+                acc1 += t;
+            }
+            for (int64_t i = (c4 << 2) + tid; i < a.clean_n; i += nth)
+                if ((int)(i % a.clean_T) != a.clean_T - 1 && i + 1 < a.clean_n) acc1 += fabsf(a.clean[i + 1] - a.clean[i]);
+        } else {
+            for (int64_t i = tid; i < a.n; i += nth) {
+                float x = stepped1<STEP, false>(a.p_in, i, s);
+                if (a.write_q) a.q_out[i] = x;
+                if ((int)(i % a.T) != a.T - 1 && i + 1 < a.n) acc0 += fabsf(stepped1<STEP, false>(a.p_in, i + 1, s) - x);
+            }
+            for (int64_t i = tid; i < a.clean_n; i += nth)
+                if ((int)(i % a.clean_T) != a.clean_T - 1 && i + 1 < a.clean_n) acc1 += fabsf(a.clean[i + 1] - a.clean[i]);
+        }
+    }
+    wide[0] = (double)acc0;
+    wide[1] = (double)acc1;
+    block_sum<2>(wide, a.partials + 2 * (int64_t)blockIdx.x);
+}
+
+// ---- kernel: finalize -- fixed-order sum of the partials, then the reference's fp32 branch ---
+struct FinalArgs {
+    const double* partials;
+    int nblocks;
+    float* scalars;
+    float eps;           // l2: epsilon; tv: tv_epsilon; snr: snr_db
+    float snr_linear_inv_unused;
+    double snr_linear;   // 10**(snr_db/10), python double
+    double n_p;          // numel(p)
+    double n_clean;      // numel(clean)
+};
+
+template <int NORM>
+__global__ void __launch_bounds__(kThreads) k_finalize(FinalArgs a) {
+    double acc[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < a.nblocks; i += kThreads) {
+        acc[0] += a.partials[2 * i];
+        acc[1] += a.partials[2 * i + 1];
+    }
+    __shared__ double tot[2];
+    block_sum<2>(acc, tot);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    float scale = 1.f, norm = 0.f, aux0 = 0.f, aux1 = 0.f;
+    if (NORM == NORM_L2) {                                   // projections.py:41-46
+        norm = sqrtf((float)tot[0]);
+        if (norm > a.eps) scale = __frcp_rn(norm) * a.eps;     // python `eps / tensor` = reciprocal()*eps
+    } else if (NORM == NORM_SNR) {                           // projections.py:11-35
+        const float p_noise = (float)(tot[0] / a.n_p);
+        const float p_sig = (float)(tot[1] / a.n_clean);
+        aux0 = p_sig;
+        aux1 = 10.f * log10f(p_sig / (p_noise + 1e-12f));
+        norm = sqrtf((float)tot[0]);
+        if (!(aux1 >= a.eps) && !(norm < 1e-8f)) {
+            const float want = sqrtf((p_sig / (float)a.snr_linear) * (float)a.n_clean);
+            scale = want / norm;
+        }
+    } else {                                                 // projections.py:56-66
+        norm = (float)tot[0];
+        aux0 = (float)tot[1];
+        aux1 = a.eps * aux0;
+        if (norm > aux1) scale = aux1 / norm;
+    }
+    a.scalars[PAA_S_SCALE] = scale;
+    a.scalars[PAA_S_NORM] = norm;
+    a.scalars[PAA_S_AUX0] = aux0;
+    a.scalars[PAA_S_AUX1] = aux1;
+}
+
+// ---- kernel: pass B -- q *= scale (skipped on the device when scale == 1 and in place) --------
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) k_scale(const float* q_in, float* p_out, int64_t n,
+                                                   const float* __restrict__ scalars) {
+    const float sc = scalars[PAA_S_SCALE];
+    if (sc == 1.f && q_in == p_out) return;
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x, nth = (int64_t)gridDim.x * kThreads;
+    if (VEC) {
+        const int64_t n4 = n >> 2;
+        for (int64_t i = tid; i < n4; i += nth) {
+            float4 x = ld4(q_in + i * 4);
+            x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
+            st4(p_out + i * 4, x);
+        }
+        for (int64_t i = (n4 << 2) + tid; i < n; i += nth) p_out[i] = q_in[i] * sc;
+    } else {
+        for (int64_t i = tid; i < n; i += nth) p_out[i] = q_in[i] * sc;
+    }
+}
+
+// ---- kernel: compose + clamp (train.py:136): x_adv[b,t] = clamp(clean[b,t] + p[b % p_rows, t]) --
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) k_compose(const float* __restrict__ clean, const float* __restrict__ p,
+                                                     float* __restrict__ out, int rows, int p_rows, int T) {
+    const int64_t n = (int64_t)rows * T;
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x, nth = (int64_t)gridDim.x * kThreads;
+    if (VEC) {
+        const int64_t n4 = n >> 2;
+        for (int64_t i4 = tid; i4 < n4; i4 += nth) {
+            const int64_t i = i4 * 4;
+            const int64_t pi = p_rows == 1 ? i % T : i;
+            float4 c = ld4_stream(clean + i), q = ld4(p + pi);
+            c.x = clamp1(c.x + q.x, -1.f, 1.f); c.y = clamp1(c.y + q.y, -1.f, 1.f);
+            c.z = clamp1(c.z + q.z, -1.f, 1.f); c.w = clamp1(c.w + q.w, -1.f, 1.f);
+            st4(out + i, c);
+        }
+    } else {
+        for (int64_t i = tid; i < n; i += nth) out[i] = clamp1(clean[i] + p[p_rows == 1 ? i % T : i], -1.f, 1.f);
+    }
+}
+
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+inline int grid_for(const paa_handle* h, int64_t n_vec) {
+    int64_t want = (n_vec + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)h->num_sms * kBlocksPerSm;
+    return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+template <int STEP>
+int launch_step_clamp(paa_handle* h, const float* p_in, float* p_out, int64_t n, float lo, float hi, bool clamp,
+                      const StepDev& sd, cudaStream_t st) {
+    bool vec = aligned16(p_in) && aligned16(p_out) && (STEP == PAA_STEP_NONE || aligned16(sd.grad)) &&
+               (STEP != PAA_STEP_ADAM || (aligned16(sd.m) && aligned16(sd.v)));
+    int grid = grid_for(h, vec ? (n + 3) / 4 : n);
+    if (vec) k_step_clamp<STEP, true><<<grid, kThreads, 0, st>>>(p_in, p_out, n, lo, hi, clamp, sd);
+    else k_step_clamp<STEP, false><<<grid, kThreads, 0, st>>>(p_in, p_out, n, lo, hi, clamp, sd);
+    PAA_LAUNCH_CHECK(h);
+    return PAA_OK;
+}
+
+template <int NORM, int STEP>
+int launch_reduce(paa_handle* h, const ReduceArgs& a, const StepDev& sd, int grid, bool vec, cudaStream_t st) {
+    if (vec) k_reduce<NORM, STEP, true><<<grid, kThreads, 0, st>>>(a, sd);
+    else k_reduce<NORM, STEP, false><<<grid, kThreads, 0, st>>>(a, sd);
+    PAA_LAUNCH_CHECK(h);
+    return PAA_OK;
+}
+
+template <int NORM>
+int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int T, const float* clean,
+                   int64_t clean_n, int clean_T, float eps, double snr_linear, const paa_step* step, void* scratch,
+                   cudaStream_t st) {
+    if (!h || !p_in || !p_out || !scratch) return PAA_ERR_NULL;
+    if (rows <= 0 || T <= 0) return PAA_ERR_SHAPE;
+    if (NORM != NORM_L2 && !clean) return PAA_ERR_NEED_CLEAN;
+    if (NORM != NORM_L2 && (clean_n <= 0 || clean_T <= 0)) return PAA_ERR_SHAPE;
+    int mode = 0;
+    StepDev sd{};
+    int rc = paa_make_step(step, &mode, &sd);
+    if (rc) return rc;
+    const int64_t n = (int64_t)rows * T;
+    const float* src = p_in;
+    if (NORM == NORM_TV && mode != PAA_STEP_NONE) {
+        if (p_in == p_out) return PAA_ERR_ALIAS;
+        if (mode == PAA_STEP_ADAM) {       // neighbour recomputation would need the pre-update state
+            rc = paa_launch_adam_prepass(h, p_in, p_out, n, sd, st);
+            if (rc) return rc;
+            src = p_out;
+            mode = PAA_STEP_NONE;
+        }
+    }
+    ReduceArgs a{};
+    a.p_in = src; a.q_out = p_out; a.n = n; a.T = T;
+    a.clean = clean; a.clean_n = NORM == NORM_L2 ? 0 : clean_n; a.clean_T = clean_T > 0 ? clean_T : 1;
+    a.partials = scratch_partials(scratch);
+    a.write_q = (mode != PAA_STEP_NONE) || (src != p_out);
+    bool vec = aligned16(src) && aligned16(p_out) && (NORM == NORM_L2 || aligned16(clean)) &&
+               (mode == PAA_STEP_NONE || aligned16(sd.grad)) &&
+               (mode != PAA_STEP_ADAM || (aligned16(sd.m) && aligned16(sd.v)));
+    int64_t work = std::max<int64_t>(n, a.clean_n);
+    int grid = std::min(grid_for(h, vec ? (work + 3) / 4 : work), kMaxPartialBlocks);
+    switch (mode) {
+        case PAA_STEP_NONE: rc = launch_reduce<NORM, PAA_STEP_NONE>(h, a, sd, grid, vec, st); break;
+        case PAA_STEP_PGD: rc = launch_reduce<NORM, PAA_STEP_PGD>(h, a, sd, grid, vec, st); break;
+        default: rc = launch_reduce<NORM, PAA_STEP_ADAM>(h, a, sd, grid, vec, st); break;
+    }
+    if (rc) return rc;
+    FinalArgs f{};
+    f.partials = a.partials; f.nblocks = grid; f.scalars = scratch_scalars(scratch);
+    f.eps = eps; f.snr_linear = snr_linear; f.n_p = (double)n; f.n_clean = (double)clean_n;
+    k_finalize<NORM><<<1, kThreads, 0, st>>>(f);
+    PAA_LAUNCH_CHECK(h);
+    bool vb = aligned16(p_out);
+    int gridb = grid_for(h, vb ? (n + 3) / 4 : n);
+    if (vb) k_scale<true><<<gridb, kThreads, 0, st>>>(p_out, p_out, n, f.scalars);
+    else k_scale<false><<<gridb, kThreads, 0, st>>>(p_out, p_out, n, f.scalars);
+    PAA_LAUNCH_CHECK(h);
+    return PAA_OK;
+}
+
+}  // namespace
+
+// Host-side folding of the Adam scalars, in double like torch/optim/adam.py:531-547, rounded to
+// fp32 only where torch applies them to fp32 tensors.
+int paa_make_step(const paa_step* step, int* mode, StepDev* out) {
+    *mode = PAA_STEP_NONE;
+    if (!step || step->mode == PAA_STEP_NONE) return PAA_OK;
+    if (step->mode != PAA_STEP_PGD && step->mode != PAA_STEP_ADAM) return PAA_ERR_UNSUPPORTED;
+    if (!step->grad) return PAA_ERR_NULL;
+    out->grad = step->grad;
+    out->lr = (float)step->lr;
+    if (step->mode == PAA_STEP_ADAM) {
+        if (!step->adam_m || !step->adam_v) return PAA_ERR_NULL;
+        if (step->adam_t < 1) return PAA_ERR_SHAPE;
+        const double b1 = step->beta1, b2 = step->beta2;
+        const double bc1 = 1.0 - std::pow(b1, (double)step->adam_t);
+        const double bc2 = 1.0 - std::pow(b2, (double)step->adam_t);
+        out->m = step->adam_m; out->v = step->adam_v;
+        out->w1 = (float)(1.0 - b1);
+        out->beta2 = (float)b2;
+        out->w2 = (float)(1.0 - b2);
+        out->neg_step = (float)(-(step->lr / bc1));
+        out->bc2_sqrt = (float)std::sqrt(bc2);
+        out->eps = (float)step->eps;
+    }
+    *mode = step->mode;
+    return PAA_OK;
+}
+
+int paa_launch_adam_prepass(paa_handle* h, const float* p_in, float* p_out, int64_t n, const StepDev& sd, cudaStream_t st) {
+    return launch_step_clamp<PAA_STEP_ADAM>(h, p_in, p_out, n, 0.f, 0.f, false, sd, st);
+}
+
+extern "C" {
+
+int paa_step_only(paa_handle* h, const float* p_in, float* p_out, int rows, int T, const paa_step* step, void* stream) {
+    if (!h || !p_in || !p_out) return PAA_ERR_NULL;
+    if (rows <= 0 || T <= 0) return PAA_ERR_SHAPE;
+    int mode = 0;
+    StepDev sd{};
+    int rc = paa_make_step(step, &mode, &sd);
+    if (rc) return rc;
+    const int64_t n = (int64_t)rows * T;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (mode) {
+        case PAA_STEP_PGD: return launch_step_clamp<PAA_STEP_PGD>(h, p_in, p_out, n, 0.f, 0.f, false, sd, st);
+        case PAA_STEP_ADAM: return launch_step_clamp<PAA_STEP_ADAM>(h, p_in, p_out, n, 0.f, 0.f, false, sd, st);
+        default: return launch_step_clamp<PAA_STEP_NONE>(h, p_in, p_out, n, 0.f, 0.f, false, sd, st);
+    }
+}
+
+int paa_project_linf(paa_handle* h, const float* p_in, float* p_out, int rows, int T, double lo, double hi,
+                     const paa_step* step, void* stream) {
+    if (!h || !p_in || !p_out) return PAA_ERR_NULL;
+    if (rows <= 0 || T <= 0) return PAA_ERR_SHAPE;
+    int mode = 0;
+    StepDev sd{};
+    int rc = paa_make_step(step, &mode, &sd);
+    if (rc) return rc;
+    const int64_t n = (int64_t)rows * T;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (mode) {
+        case PAA_STEP_PGD: return launch_step_clamp<PAA_STEP_PGD>(h, p_in, p_out, n, (float)lo, (float)hi, true, sd, st);
+        case PAA_STEP_ADAM: return launch_step_clamp<PAA_STEP_ADAM>(h, p_in, p_out, n, (float)lo, (float)hi, true, sd, st);
+        default: return launch_step_clamp<PAA_STEP_NONE>(h, p_in, p_out, n, (float)lo, (float)hi, true, sd, st);
+    }
+}
+
+int paa_project_l2(paa_handle* h, const float* p_in, float* p_out, int rows, int T, double epsilon,
+                   const paa_step* step, void* scratch, void* stream) {
+    return project_reduce<NORM_L2>(h, p_in, p_out, rows, T, nullptr, 0, 1, (float)epsilon, 0.0, step, scratch,
+                                   (cudaStream_t)stream);
+}
+
+int paa_project_snr(paa_handle* h, const float* p_in, float* p_out, int rows, int T, const float* clean,
+                    int64_t clean_numel, double snr_db, const paa_step* step, void* scratch, void* stream) {
+    return project_reduce<NORM_SNR>(h, p_in, p_out, rows, T, clean, clean_numel, 1, (float)snr_db,
+                                    std::pow(10.0, snr_db / 10.0), step, scratch, (cudaStream_t)stream);
+}
+
+int paa_project_tv(paa_handle* h, const float* p_in, float* p_out, int rows, int T, const float* clean,
+                   int clean_rows, int clean_T, double tv_epsilon, const paa_step* step, void* scratch, void* stream) {
+    return project_reduce<NORM_TV>(h, p_in, p_out, rows, T, clean, (int64_t)clean_rows * clean_T, clean_T,
+                                   (float)tv_epsilon, 0.0, step, scratch, (cudaStream_t)stream);
+}
+
+int paa_compose_clamp(paa_handle* h, const float* clean, int clean_rows, const float* p, int p_rows, int T,
+                      float* x_adv, void* stream) {
+    if (!h || !clean || !p || !x_adv) return PAA_ERR_NULL;
+    if (clean_rows <= 0 || T <= 0 || (p_rows != 1 && p_rows != clean_rows)) return PAA_ERR_SHAPE;
+    const int64_t n = (int64_t)clean_rows * T;
+    bool vec = aligned16(clean) && aligned16(p) && aligned16(x_adv) && (T % 4 == 0);
+    int grid = grid_for(h, vec ? (n + 3) / 4 : n);
+    if (vec) k_compose<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(clean, p, x_adv, clean_rows, p_rows, T);
+    else k_compose<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(clean, p, x_adv, clean_rows, p_rows, T);
+    PAA_LAUNCH_CHECK(h);
+    return PAA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,167 @@
+"""The per-iteration perturbation update with the reference's entry points
+(src/training_utils/train.py:27-182): ``perturbation_constraint`` keeps its signature, and
+``step_and_project`` is the fused form (optimiser step + projection in the same kernels) that
+``train_epoch`` uses."""
+import logging
+import time
+from dataclasses import dataclass
+from datetime import datetime
+from typing import Iterable, Optional
+
+import torch
+
+try:
+    from .. import paa_lib as L
+    from ..core import projections
+except ImportError:
+    import paa_lib as L
+    from core import projections
+
+logger = logging.getLogger("asr_attack")
+
+FREQ_NORMS = ("fletcher_munson", "min_max_freqs", "max_phon")
+
+
+@dataclass(frozen=True)
+class TrainEpochResult:
+    p: torch.Tensor
+    avg_ctc: float
+    avg_wer: float
+
+    def __iter__(self):          # lets ``p, ctc, wer = train_epoch(...)`` work (run_attack.py:64)
+        return iter((self.p, self.avg_ctc, self.avg_wer))
+
+
+def _avg(values: Iterable[float]) -> float:
+    vals = list(values)
+    return sum(vals) / max(len(vals), 1)
+
+
+def _frequency_domain(p, clean_audio, args, interp, spl_thresh, step):
+    """STFT -> per-bin projection -> ISTFT -> length alignment (train.py:38-66, :27-35), one fused kernel
+    for min_max_freqs / max_phon and two passes for fletcher_munson."""
+    x = L.f32c(p.detach().reshape(-1, p.shape[-1]))
+    plan = L.plan_for(x, args)
+    rows, T = x.shape
+    frames = 1 + T // plan.hop
+    out_len = plan.hop * (frames - 1) if clean_audio is None else int(clean_audio.shape[-1])
+    out = torch.empty((rows, out_len), dtype=torch.float32, device=x.device)
+    scratch = plan.scratch(rows, T)
+    stream = L.stream_ptr(x.device)
+    kind = args.norm_type
+    if kind == "min_max_freqs":
+        rc = L.lib.paa_project_min_max_freqs(plan.h, x.data_ptr(), out.data_ptr(), rows, T, out_len,
+                                             float(args.min_freq_attack), float(args.max_freq_attack),
+                                             L.step_ref(step), scratch, stream)
+    elif kind == "max_phon":
+        L.need_cuda(spl_thresh)
+        thr = L.f32c(spl_thresh.detach().reshape(-1))
+        if thr.numel() != plan.n_fft // 2 + 1:
+            raise RuntimeError(f"spl_thresh has {thr.numel()} bins, expected {plan.n_fft // 2 + 1}")
+        rc = L.lib.paa_project_max_phon(plan.h, x.data_ptr(), out.data_ptr(), rows, T, out_len, thr.data_ptr(),
+                                        float(args.phon_reference_db), L.step_ref(step), scratch, stream)
+    elif kind == "fletcher_munson":
+        plan.set_fm_grid(interp)
+        exact = 0 if getattr(args, "fm_identity_roundtrip", False) else 1
+        rc = L.lib.paa_project_fletcher_munson(plan.h, x.data_ptr(), out.data_ptr(), rows, T, out_len,
+                                               float(args.fm_epsilon), exact, L.step_ref(step), scratch, stream)
+    else:
+        raise ValueError(f"Unsupported frequency-domain norm_type: {kind!r}")
+    L.check(rc, plan.h)
+    return out.reshape(p.shape[:-1] + (out_len,))
+
+
+def _dispatch(p, clean_audio, args, interp, spl_thresh, step):
+    kind = args.norm_type
+    if kind in FREQ_NORMS:
+        return _frequency_domain(p, clean_audio, args, interp, spl_thresh, step)
+    if kind == "l2":
+        return projections.project_l2(p, args.l2_size, _step=step)
+    if kind == "linf":
+        return projections.project_linf(p, -args.linf_size, args.linf_size, _step=step)
+    if kind == "snr":
+        if clean_audio is None:
+            raise ValueError("SNR projection requires clean_audio ro compare to")
+        return projections.project_snr(clean=clean_audio, perturbation=p, snr_db=args.snr_db, _step=step)
+    if kind == "tv":
+        if clean_audio is None:
+            raise ValueError("TV projection can benefit from clean_audio for bounds")
+        return projections.project_tv(p=p, args=args, clean_audio=clean_audio, _step=step)
+    raise ValueError(f"Unknown norm_type: {kind!r}")
+
+
+def perturbation_constraint(p, clean_audio, args, interp, spl_thresh):
+    """Project perturbation p into the feasible set named by args.norm_type (train.py:69-99).
+    Returns a new tensor; no autograd graph is attached."""
+    L.need_cuda(p, clean_audio)
+    with torch.no_grad():
+        return _dispatch(p, clean_audio, args, interp, spl_thresh, None)
+
+
+def step_and_project(p, grad, clean_audio, args, interp, spl_thresh, optimizer: Optional[torch.optim.Optimizer] = None):
+    """One fused hot-path iteration: the optimiser step of train.py:155-175 on ``p`` given ``grad`` (= p.grad as
+    autograd left it), then the projection -- in the same kernels, without host synchronisation.
+
+    pgd : p + args.lr * sign(grad)                       (train.py:161)
+    adam: torch.optim.Adam arithmetic on the optimiser's own state tensors (exp_avg, exp_avg_sq, step) and
+          its current param_group lr, so StepLR and state_dict keep working (build.py:352-359).
+    """
+    L.need_cuda(p, grad, clean_audio)
+    with torch.no_grad():
+        g = L.f32c(grad.detach())
+        if g.shape != p.shape:
+            raise RuntimeError(f"grad shape {tuple(g.shape)} != p shape {tuple(p.shape)}")
+        if args.optimizer_type == "pgd":
+            step = L.make_step(L.STEP_PGD, g, args.lr)
+        elif args.optimizer_type == "adam":
+            if optimizer is None:
+                raise ValueError("Adam optimizer selected but optimizer is None")
+            step = optimizer.fused_step_descriptor(p, g)
+        else:
+            raise NotImplementedError(f"Optimization type not implemented: {args.optimizer_type!r}")
+        return _dispatch(p, clean_audio, args, interp, spl_thresh, step)
+
+
+def train_epoch(args, train_data_loader, p, model, epoch, processor, interp, wer_metric, spl_thresh, optimizer):
+    """One epoch optimising a universal perturbation over the loader -- the loop of train.py:103-182 with the
+    step + projection replaced by the fused call.  The wav2vec2 forward/backward stays on PyTorch."""
+    try:
+        from ..core import loss_helpers
+    except ImportError:
+        from core import loss_helpers
+    ctc_scores, wer_scores, times = [], [], []
+    model.eval()
+    logger.info("timestamp: %s | starting epoch: %d", datetime.now(), epoch)
+    direction = +1 if args.attack_mode == "untargeted" else -1
+
+    for clean_audio, target_texts in train_data_loader:
+        t0 = time.perf_counter()
+        clean_audio = clean_audio.to(args.device, non_blocking=True)
+        clean_audio.requires_grad_(False)
+        p.requires_grad_(True)
+        if p.grad is not None:
+            p.grad = None
+        perturbed = (clean_audio + p).clamp_(-1.0, 1.0)
+        loss, logits = loss_helpers.get_loss_for_training(model=model, data=perturbed, target_texts=target_texts,
+                                                          processor=processor, args=args)
+        ctc_scores.append(float(loss.item()))
+        with torch.inference_mode():
+            wer = loss_helpers.compute_wer(logits=logits, target_texts=target_texts, processor=processor,
+                                           wer_metric=wer_metric)
+        wer_scores.append(float(wer))
+
+        if args.optimizer_type == "pgd":
+            (direction * loss).backward()
+            p = step_and_project(p, p.grad, clean_audio, args, interp, spl_thresh).detach()
+        elif args.optimizer_type == "adam":
+            if optimizer is None:
+                raise ValueError("Adam optimizer selected but optimizer is None")
+            optimizer.zero_grad(set_to_none=True)
+            (-1 * direction * loss).backward()
+            with torch.no_grad():
+                p.data = step_and_project(p.data, p.grad, clean_audio, args, interp, spl_thresh, optimizer=optimizer)
+        else:
+            raise NotImplementedError(f"Optimization type not implemented: {args.optimizer_type!r}")
+        times.append(time.perf_counter() - t0)
+
+    return TrainEpochResult(p=p, avg_ctc=_avg(ctc_scores), avg_wer=_avg(wer_scores))

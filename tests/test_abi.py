@@ -1,0 +1,101 @@
+"""CPU-side checks of the C ABI: libpaa.so loads, exports every symbol include/paa.h declares, and its
+host-only entry points (ISO-226 tables, WER counters, argument validation) agree with the reference's
+golden vectors.  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+import paa_b200
+from paa_b200 import paa_lib as L
+from paa_b200.core import iso
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "paa.h")).read()
+    declared = set(re.findall(r"\b(paa_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(L.EXPORTS)
+    lib = C.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert L.lib.paa_version() >= 100
+    assert L.lib.paa_status_string(0) == b"ok"
+
+
+def test_iso_tables_against_reference():
+    g = load_golden("iso_tables")
+    for i, ph in enumerate(g["phons"]):
+        got = L.iso226_spl(float(ph), g["freqs"])
+        assert np.abs(got - g["spl"][i]).max() < 1e-9
+    ph, fk, w = L.weight_grid()
+    assert np.array_equal(ph, g["grid_phon"]) and np.array_equal(fk, g["grid_freq"])
+    assert np.abs(w - g["grid_w"]).max() < 1e-12
+    it = iso.build_weight_interpolator()
+    assert np.abs(it(g["query"]) - g["query_w"]).max() < 1e-12
+    for n_fft in (512, 1024):
+        for phon in (20.0, 35.5):
+            got = L.spl_thresh(n_fft, 16000, phon)
+            assert np.abs(got - g[f"thr_{n_fft}_{phon}"]).max() < 1e-3      # phon tolerance of north_star
+            assert np.array_equal(got, g[f"thr_{n_fft}_{phon}"])
+
+
+def test_iso_class_mirrors_reference_behaviour():
+    assert abs(iso.ISO226(20)(np.array([1000.0]))[0] - 20.00517) < 1e-5
+    assert iso.ISO226(40)(np.array([100]))[0] == 64                      # integer in, truncated out
+    for bad in (-1, 90.5):
+        with pytest.raises(ValueError):
+            iso.ISO226(bad)
+    for bad in (19.0, 20001.0):
+        with pytest.raises(ValueError):
+            iso.ISO226(40)(np.array([bad]))
+    f, p, spl = iso.compute_iso226_weight_matrix()
+    assert spl.shape == (10, 30) and abs(spl.max() - 123.70539502730307) < 1e-9
+    w = iso.perceptual_weight(spl)
+    np.testing.assert_allclose(w[:, 17], [1, 0.844866, 0.70272, 0.573687, 0.457747, 0.354888, 0.265105, 0.188394,
+                                          0.124754, 0.074184], atol=1e-6)
+
+
+def test_status_codes_without_gpu():
+    out = np.empty(1)
+    f = np.array([10.0])
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))           # noqa: E731
+    assert L.lib.paa_iso226_spl(40.0, dp(f), 1, dp(out)) == L.ERR_RANGE
+    assert L.lib.paa_iso226_spl(95.0, dp(np.array([100.0])), 1, dp(out)) == L.ERR_RANGE
+    assert L.lib.paa_iso226_spl(40.0, None, 1, dp(out)) == L.ERR_NULL
+    h = C.c_void_p()
+    assert L.lib.paa_create(0, 768, 256, 16000, C.byref(h)) == L.ERR_UNSUPPORTED
+    assert L.lib.paa_create(0, 1024, 300, 16000, C.byref(h)) == L.ERR_UNSUPPORTED
+    assert L.lib.paa_create(0, 1024, 256, 16000, None) == L.ERR_NULL
+    assert L.lib.paa_destroy(None) == L.OK
+    assert L.lib.paa_scratch_bytes(None, 1, 1) == 0
+    with pytest.raises(ValueError):
+        L.check(L.ERR_NEED_CLEAN)
+    with pytest.raises(ValueError):
+        L.check(L.ERR_RANGE)
+    with pytest.raises(RuntimeError):
+        L.check(L.ERR_NOLA)
+    with pytest.raises(L.PaaError):
+        L.check(L.ERR_ALIAS)
+
+
+def test_wer_counts():
+    assert L.wer_counts(["a b c"], ["a b c"]) == (0, 3)
+    assert L.wer_counts(["a b c", "hello world"], ["a x c d", ""]) == (4, 5)
+    assert L.wer_counts(["  spaced   out  "], ["spaced out"]) == (0, 2)
+    assert L.wer_counts([], []) == (0, 0)
+    from paa_b200.core.loss_helpers import WerMetric
+    m = WerMetric()
+    assert m.compute(predictions=["a"], references=["a b"]) == 0.5
+    assert (m.errors, m.words) == (1, 2)
+
+
+def test_cpu_tensors_are_refused():
+    import torch
+    args = paa_b200.training_utils.parser.create_arg_parser().parse_args(["--norm_type", "l2"])
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        paa_b200.perturbation_constraint(torch.zeros(1, 4096), None, args, None, None)
