@@ -71,6 +71,8 @@ enum {
 
 const char* paa_status_string(int status);
 int         paa_version(void);
+/* Number of CUDA kernels this library has launched in this process (all handles, all streams). */
+int64_t     paa_launch_count(void);
 
 /* ---- handle ------------------------------------------------------------------------------ */
 int paa_create(int device, int n_fft, int hop, int sr, paa_handle** out);

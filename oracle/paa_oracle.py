@@ -475,4 +475,4 @@ def attack_iteration(model, p, clean, texts, hp, interp=None, spl_thresh=None, a
     (sign * out.loss).backward()
     with torch.no_grad():
         p_new = step_and_constrain(p.detach(), p.grad, clean, hp, interp, spl_thresh, adam, lr)
-    return p_new.detach(), float(out.loss), greedy_transcripts(out.logits.detach())
+    return p_new.detach(), float(out.loss.detach()), greedy_transcripts(out.logits.detach())

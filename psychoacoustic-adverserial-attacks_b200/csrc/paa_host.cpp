@@ -9,6 +9,8 @@
 #include <vector>
 #include "paa_internal.h"
 
+long long g_paa_launches = 0;
+
 namespace {
 
 constexpr int kBands = 29;
@@ -99,6 +101,7 @@ const char* paa_status_string(int s) {
 }
 
 int paa_version(void) { return PAA_VERSION; }
+int64_t paa_launch_count(void) { return (int64_t)__atomic_load_n(&g_paa_launches, __ATOMIC_RELAXED); }
 
 int paa_iso226_spl(double phon, const double* freqs_hz, int n, double* out) {
     if (!freqs_hz || !out) return PAA_ERR_NULL;

@@ -45,7 +45,12 @@ static inline int paa_cuda_fail(const paa_handle* h, cudaError_t e) {
         cudaError_t e__ = (call);                                      \
         if (e__ != cudaSuccess) return paa_cuda_fail((h), e__);        \
     } while (0)
-#define PAA_LAUNCH_CHECK(h) PAA_CUDA((h), cudaGetLastError())
+extern long long g_paa_launches;       // bumped by every kernel launch (paa_launch_count)
+#define PAA_LAUNCH_CHECK(h)                        \
+    do {                                           \
+        __atomic_add_fetch(&g_paa_launches, 1, __ATOMIC_RELAXED); \
+        PAA_CUDA((h), cudaGetLastError());         \
+    } while (0)
 
 // ---- scratch layout (bytes) -----------------------------------------------------------------
 // [0,256)            float scalars[PAA_S_COUNT..]           (PAA_S_* indices)

@@ -23,7 +23,7 @@ STEP_NONE, STEP_PGD, STEP_ADAM = 0, 1, 2
 S_SCALE, S_NORM, S_AUX0, S_AUX1 = 0, 1, 2, 3
 
 EXPORTS = (
-    "paa_status_string paa_version paa_create paa_destroy paa_last_cuda_error paa_num_bins paa_num_frames "
+    "paa_status_string paa_version paa_launch_count paa_create paa_destroy paa_last_cuda_error paa_num_bins paa_num_frames "
     "paa_scratch_bytes paa_scalars paa_iso226_spl paa_weight_grid paa_spl_thresh paa_interp2 paa_set_fm_grid "
     "paa_project_linf paa_project_l2 paa_project_snr paa_project_tv paa_project_min_max_freqs "
     "paa_project_max_phon paa_project_fletcher_munson paa_step_only paa_stft paa_istft "
@@ -51,6 +51,7 @@ def _load() -> C.CDLL:
     sig = {
         "paa_status_string": (C.c_char_p, [i32]),
         "paa_version": (i32, []),
+        "paa_launch_count": (i64, []),
         "paa_create": (i32, [i32, i32, i32, i32, C.POINTER(vp)]),
         "paa_destroy": (i32, [vp]),
         "paa_last_cuda_error": (i32, [vp]),
