@@ -4,44 +4,42 @@
 // (z[m] = x[2m] + i x[2m+1]) followed by the usual split into the n_fft/2+1 one-sided bins.
 // The complex FFT is a three-stage Stockham autosort (radix 8*8*8 for N=512, 4*8*8 for N=256):
 // every lane owns N/32 points per stage in registers, stages exchange through a warp-private
-// shared-memory buffer of N float2, and only __syncwarp is needed.  The buffer index is XOR
-// swizzled so that every stage's strided stores and contiguous loads are bank-conflict free for
-// 64-bit accesses (checked exhaustively by tools/bank_search.py).
+// shared-memory buffer of float2, and only __syncwarp is needed.
+//
+// Buffer layout: logical point i lives at pad(i) = i + (i >> 4) (one spare slot per 16).  The pad is additive, so
+// every access of a stage is  (one per-lane base register) + (compile-time offset)  and costs no
+// address arithmetic; the contiguous loads stay conflict free and the strided stores of the first
+// two stages are at worst 2-way conflicted (tools/bank_search.py).  The kernel is issue-bound, not
+// shared-memory-bandwidth bound, which is why this beats a conflict-free XOR swizzle here.
 #pragma once
 #include <cuda_runtime.h>
 
 namespace paa {
 
 template <int NFFT> struct Plan;
-template <> struct Plan<1024> {
-    static constexpr int N = 512, R0 = 8, R1 = 8, R2 = 8;
-    __device__ __forceinline__ static int swz(int i) {
-        return i ^ (((i >> 4) & 1) | (((i >> 5) & 1) << 1) | (((i >> 6) & 1) * 12));
-    }
-};
-template <> struct Plan<512> {
-    static constexpr int N = 256, R0 = 4, R1 = 8, R2 = 8;
-    __device__ __forceinline__ static int swz(int i) {
-        return i ^ (((i >> 4) & 1) | (((i >> 5) & 1) * 6) | (((i >> 6) & 1) * 8));
-    }
-};
+template <> struct Plan<1024> { static constexpr int N = 512, R0 = 8, R1 = 8, R2 = 8; };
+template <> struct Plan<512>  { static constexpr int N = 256, R0 = 4, R1 = 8, R2 = 8; };
 
-// per-lane twiddle table: stage 1 block then stage 2 block, each [NB][R-1][32] float2
+__host__ __device__ constexpr int padc(int i) { return i + (i >> 4); }
+template <int NFFT> struct BufLayout { static constexpr int kFloat2 = Plan<NFFT>::N + Plan<NFFT>::N / 16; };
+
+// per-lane twiddle table: stage 1 block [4][32] (k = j mod R0 does not depend on b) then stage 2 block
+// [NB2][4][32], float4 entries holding the forward twiddles (cos, -sin) of r = 2q and r = 2q+1
 template <int NFFT> struct TwLayout {
     using P = Plan<NFFT>;
     static constexpr int NB1 = P::N / P::R1 / 32, NB2 = P::N / P::R2 / 32;
-    static constexpr int kStage1 = NB1 * (P::R1 - 1) * 32;
-    static constexpr int kStage2 = NB2 * (P::R2 - 1) * 32;
-    static constexpr int kTotal = kStage1 + kStage2;     // float2 entries
+    static constexpr int kStage1 = 4 * 32;               // float4 entries
+    static constexpr int kStage2 = NB2 * 4 * 32;
+    static constexpr int kTotal = kStage1 + kStage2;
 };
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 // multiply by w (forward, DIR=-1) or conj(w) (inverse, DIR=+1); tables hold forward twiddles (cos, -sin)
 template <int DIR>
-__device__ __forceinline__ float2 cmul_tw(float2 v, float2 w) {
-    if (DIR < 0) return make_float2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
-    return make_float2(v.x * w.x + v.y * w.y, v.y * w.x - v.x * w.y);
+__device__ __forceinline__ float2 cmul_tw(float2 v, float wx, float wy) {
+    if (DIR < 0) return make_float2(v.x * wx - v.y * wy, v.x * wy + v.y * wx);
+    return make_float2(v.x * wx + v.y * wy, v.y * wx - v.x * wy);
 }
 // multiply by -i (forward) / +i (inverse)
 template <int DIR>
@@ -85,74 +83,93 @@ template <int DIR> struct Dft<8, DIR> {
     __device__ __forceinline__ static void run(float2 (&v)[8]) { dft8<DIR>(v); }
 };
 
+// Per-lane base offsets into the padded buffer (float2 units), computed once per warp.
+//   ld : contiguous accesses  lane + c, c a multiple of 32          -> ld + padc(c)
+//   s0 : stage-0 stores       R0*j + r,  j = lane + 32 b            -> s0 + r + padc(32*R0*b)
+//   s1 : stage-1 stores       (j/R0)*R0*R1 + j%R0 + r*R0            -> s1 + padc(r*R0) + padc(32*R1*b)
+template <int NFFT>
+struct LaneBase {
+    int ld, s0, s1;
+    __device__ __forceinline__ explicit LaneBase(int lane) {
+        using P = Plan<NFFT>;
+        ld = padc(lane);
+        s0 = padc(P::R0 * lane);
+        const int i1 = (lane / P::R0) * P::R0 * P::R1 + (lane % P::R0);
+        s1 = padc(i1);
+    }
+};
+
 // One Stockham stage on register data: twiddle (k = j mod Ns), R-point DFT.
 // v[b][r] holds input j + r*N/R of butterfly j = lane + 32 b.
-template <int N, int R, int Ns, int DIR>
-__device__ __forceinline__ void stage_compute(float2 (&v)[N / R / 32][R], const float2* __restrict__ tw, int lane) {
+template <int N, int R, bool TWIDDLE, bool PER_B, int DIR>
+__device__ __forceinline__ void stage_compute(float2 (&v)[N / R / 32][R], const float4* __restrict__ tw, int lane) {
     constexpr int NB = N / R / 32;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        if (Ns > 1) {
+        if (TWIDDLE) {
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[b][r] = cmul_tw<DIR>(v[b][r], tw[(b * (R - 1) + (r - 1)) * 32 + lane]);
+            for (int q = 0; q < R / 2; ++q) {
+                const float4 w = tw[((PER_B ? b : 0) * 4 + q) * 32 + lane];
+                if (q > 0) v[b][2 * q] = cmul_tw<DIR>(v[b][2 * q], w.x, w.y);
+                v[b][2 * q + 1] = cmul_tw<DIR>(v[b][2 * q + 1], w.z, w.w);
+            }
         }
         Dft<R, DIR>::run(v[b]);
     }
 }
-template <class P, int R>
-__device__ __forceinline__ void stage_load(float2 (&v)[P::N / R / 32][R], const float2* buf, int lane) {
-#pragma unroll
-    for (int b = 0; b < P::N / R / 32; ++b)
-#pragma unroll
-        for (int r = 0; r < R; ++r) v[b][r] = buf[P::swz(lane + 32 * b + r * (P::N / R))];
-}
-// output r of butterfly j goes to (j/Ns)*Ns*R + (j%Ns) + r*Ns
-template <class P, int R, int Ns>
-__device__ __forceinline__ void stage_store(const float2 (&v)[P::N / R / 32][R], float2* buf, int lane) {
-#pragma unroll
-    for (int b = 0; b < P::N / R / 32; ++b) {
-        const int j = lane + 32 * b;
-        const int base = (j / Ns) * Ns * R + (j % Ns);
-#pragma unroll
-        for (int r = 0; r < R; ++r) buf[P::swz(base + r * Ns)] = v[b][r];
-    }
-}
 
-// Complex FFT of N points.  First-stage inputs come from `first` (functor m -> float2), the
-// result of the last stage is handed to `last` (functor (m, float2)) in natural order m.
+// Complex FFT of N points.  First-stage inputs come from `first` (functor (m, c) -> float2) and the
+// result of the last stage is handed to `last` (functor (m, c, float2)) in natural order; m = lane + c
+// with c a compile-time multiple of 32, so callers can address  base(lane) + padc(c).
 template <int NFFT, int DIR, class First, class Last>
-__device__ __forceinline__ void fft_warp(float2* buf, const float2* __restrict__ tw, int lane, First first, Last last) {
+__device__ __forceinline__ void fft_warp(float2* buf, const float4* __restrict__ tw, int lane, const LaneBase<NFFT>& lb,
+                                         First first, Last last) {
     using P = Plan<NFFT>;
     using L = TwLayout<NFFT>;
     constexpr int N = P::N;
     {   // stage 0: Ns = 1, no twiddles
-        float2 v[N / P::R0 / 32][P::R0];
+        constexpr int R = P::R0, NB = N / R / 32;
+        float2 v[NB][R];
 #pragma unroll
-        for (int b = 0; b < N / P::R0 / 32; ++b)
+        for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int r = 0; r < P::R0; ++r) v[b][r] = first(lane + 32 * b + r * (N / P::R0));
-        stage_compute<N, P::R0, 1, DIR>(v, tw, lane);
+            for (int r = 0; r < R; ++r) v[b][r] = first(lane + 32 * b + r * (N / R), 32 * b + r * (N / R));
+        stage_compute<N, R, false, false, DIR>(v, tw, lane);
         __syncwarp();                       // buf may still be read by the previous user
-        stage_store<P, P::R0, 1>(v, buf, lane);
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int r = 0; r < R; ++r) buf[lb.s0 + r + padc(32 * R * b)] = v[b][r];
     }
     __syncwarp();
     {   // stage 1: Ns = R0
-        float2 v[N / P::R1 / 32][P::R1];
-        stage_load<P, P::R1>(v, buf, lane);
-        stage_compute<N, P::R1, P::R0, DIR>(v, tw, lane);
+        constexpr int R = P::R1, NB = N / R / 32;
+        float2 v[NB][R];
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[b][r] = buf[lb.ld + padc(32 * b + r * (N / R))];
+        stage_compute<N, R, true, false, DIR>(v, tw, lane);
         __syncwarp();
-        stage_store<P, P::R1, P::R0>(v, buf, lane);
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int r = 0; r < R; ++r) buf[lb.s1 + padc(r * P::R0) + padc(32 * R * b)] = v[b][r];
     }
     __syncwarp();
     {   // stage 2: Ns = R0*R1 = N/R2, outputs j + r*Ns in natural order
-        float2 v[N / P::R2 / 32][P::R2];
-        stage_load<P, P::R2>(v, buf, lane);
-        stage_compute<N, P::R2, P::R0 * P::R1, DIR>(v, tw + L::kStage1, lane);
+        constexpr int R = P::R2, NB = N / R / 32;
+        float2 v[NB][R];
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[b][r] = buf[lb.ld + padc(32 * b + r * (N / R))];
+        stage_compute<N, R, true, true, DIR>(v, tw + L::kStage1, lane);
         __syncwarp();
 #pragma unroll
-        for (int b = 0; b < N / P::R2 / 32; ++b)
+        for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int r = 0; r < P::R2; ++r) last(lane + 32 * b + r * (P::R0 * P::R1), v[b][r]);
+            for (int r = 0; r < R; ++r) last(lane + 32 * b + r * (P::R0 * P::R1), 32 * b + r * (P::R0 * P::R1), v[b][r]);
     }
 }
 

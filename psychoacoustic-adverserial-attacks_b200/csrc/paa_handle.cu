@@ -20,17 +20,18 @@ std::vector<float> hann_periodic(int n) {
 }
 
 // Per-lane Stockham twiddles: stage with radix R after Ns points: W_{Ns*R}^{(j mod Ns) * r},
-// j = lane + 32*b, stored [b][r-1][lane] as (cos, -sin) -- the forward sign.
+// j = lane + 32*b, stored [b][q][lane] as float4 = forward twiddles (cos, -sin) of r = 2q and 2q+1.
 void stage_twiddles(std::vector<float>& out, int N, int R, int Ns) {
-    const int NB = N / R / 32;
+    const int NB = (32 % Ns == 0) ? 1 : N / R / 32;       // k = j mod Ns is the same for every b when Ns | 32
     for (int b = 0; b < NB; ++b)
-        for (int r = 1; r < R; ++r)
-            for (int lane = 0; lane < 32; ++lane) {
-                const int k = (lane + 32 * b) % Ns;
-                const double th = 2.0 * M_PI * (double)k * (double)r / (double)(Ns * R);
-                out.push_back((float)std::cos(th));
-                out.push_back((float)(-std::sin(th)));
-            }
+        for (int q = 0; q < 4; ++q)
+            for (int lane = 0; lane < 32; ++lane)
+                for (int r = 2 * q; r < 2 * q + 2; ++r) {
+                    const int k = (lane + 32 * b) % Ns;
+                    const double th = 2.0 * M_PI * (double)k * (double)(r % R) / (double)(Ns * R);
+                    out.push_back((float)std::cos(th));
+                    out.push_back((float)(-std::sin(th)));
+                }
 }
 
 template <int NFFT>

@@ -16,6 +16,7 @@ struct paa_handle {
     int num_sms = 148;
     float bin_hz = 0.f;      // fp32(1/(n_fft*(1/sr))): what torch.fft.rfftfreq multiplies arange by
     mutable int last_cuda_error = 0;
+    int no_coop = 0;         // set if the device refused a cooperative launch: use the three-kernel form
 
     // one device blob, copied into shared memory by a 1-D TMA bulk copy at kernel start:
     //   [window n_fft f32][twiddles (per-lane, stages 1..2) float2][post twiddles N/2+1 float2]

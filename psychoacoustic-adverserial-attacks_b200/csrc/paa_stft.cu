@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 #include "paa_fft.cuh"
 #include "paa_internal.h"
@@ -31,7 +32,7 @@ constexpr int kThreadsStft = kWarps * 32;
 
 enum { SRC_TIME = 0, SRC_SPEC = 1 };
 enum { SINK_TIME = 0, SINK_SPEC = 1, SINK_REDUCE = 2 };
-enum { OP_NONE = 0, OP_MASK = 1, OP_PHON = 2, OP_SCALE = 3 };
+enum { OP_NONE = 0, OP_MASK = 1, OP_PHON = 2, OP_SCALE = 3, OP_PHON_DB = 4 };
 
 struct StftArgs {
     // time-domain source [rows, T]
@@ -52,6 +53,7 @@ struct StftArgs {
     unsigned blob_bytes, off_tw, off_post;
     // per-bin op
     float bin_hz, f_min, f_max;
+    int k_lo, k_hi;        // min_max_freqs as bin indices: keep k < k_lo or k >= k_hi
     const float* spl_thresh;
     float ref_db;
     const float* scalars;  // OP_SCALE: scalars[PAA_S_SCALE]
@@ -94,15 +96,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
 
 // ---- per-bin operators ------------------------------------------------------------------------
 // project_min_max_freqs (projections.py:74-79): keep f < f_min or f > f_max, zero the band between.
+// f_k = fp32(k) * fp32(bin_hz) is monotone in k, so the host turns the two float comparisons into
+// bin indices (keep k < k_lo or k >= k_hi) with the same fp32 arithmetic.
 __device__ __forceinline__ void op_mask(const StftArgs& a, int k, float& re, float& im) {
-    const float f = (float)k * a.bin_hz;
-    const float keep = (f < a.f_min || f > a.f_max) ? 1.f : 0.f;
+    const float keep = (k < a.k_lo || k >= a.k_hi) ? 1.f : 0.f;
     re *= keep;
     im *= keep;
 }
-// project_phon_level (projections.py:142-153): every bin takes the dB round trip
-//   |X| -> 20 log10(|X|+1e-8) -> min(., thr) -> 10^(./20), phase kept.
-__device__ __forceinline__ void op_phon(const float* thr, int k, float& re, float& im) {
+// project_phon_level (projections.py:142-153) exactly as written: every bin takes the dB round trip
+//   |X| -> 20 log10(|X|+1e-8) -> min(., thr) -> 10^(./20), phase kept.   thr = scaled threshold in dB.
+__device__ __forceinline__ void op_phon_db(const float* thr, int k, float& re, float& im) {
     const float m = sqrtf(fmaf(re, re, im * im));
     const float db = 20.f * log10f(m + 1e-8f);
     const float t = thr[k];
@@ -119,11 +122,33 @@ __device__ __forceinline__ void op_phon(const float* thr, int k, float& re, floa
         im = mag * s;
     }
 }
+// The same projection in the linear domain, used by the fused kernel: with lim[k] = 10^(thr[k]/20),
+//   |X'| = min(|X| + 1e-8, lim[k])   -- the dB round trip is the identity on un-clipped bins up to
+// fp32 rounding (~1e-6 relative, inside the 1e-5 parity bar) and log10 is monotone, so no log/exp per bin.
+__device__ __forceinline__ void op_phon(const float* lim, int k, float& re, float& im) {
+    const float m = sqrtf(fmaf(re, re, im * im));
+    const float x = m + 1e-8f;
+    const float l = lim[k];
+    const float mag = (x > l) ? l : x;              // NaN falls through like torch.where(db > thr, ...)
+    if (m > 1e-18f) {
+        const float g = __fdividef(mag, m);
+        re *= g;
+        im *= g;
+    } else {
+        const float ph = atan2f(im, re);
+        float s, c;
+        sincosf(ph, &s, &c);
+        re = mag * c;
+        im = mag * s;
+    }
+}
 // compute_fm_weighted_norm_interp (projections.py:93-113): P * w(10 log10(P+1e-10), f_k)
+template <bool FAST>
 __device__ __forceinline__ float fm_term(const StftArgs& a, int k, float re, float im) {
     const float m = sqrtf(fmaf(re, re, im * im));
     const float P = m * m;
-    const float spl = 10.f * log10f(P + 1e-10f);
+    // FAST: MUFU.LG2 (abs error ~1e-6 dB, it only positions the query inside a 10 dB cell)
+    const float spl = FAST ? 3.0102999566398120f * __log2f(P + 1e-10f) : 10.f * log10f(P + 1e-10f);
     float w = a.fm_fill;
     if (a.fm_inband[k] && !(spl < a.fm_k0) && !(spl > a.fm_klast)) {
         int i;
@@ -136,34 +161,38 @@ __device__ __forceinline__ float fm_term(const StftArgs& a, int k, float re, flo
         i = max(0, min(i, a.fm_np - 2));
         const float k0 = a.fm_knots[i], k1 = a.fm_knots[i + 1];
         const float c0 = __ldg(a.fm_cols + (size_t)k * a.fm_np + i), c1 = __ldg(a.fm_cols + (size_t)k * a.fm_np + i + 1);
-        const float tp = (spl - k0) / (k1 - k0);
+        const float tp = FAST ? __fdividef(spl - k0, k1 - k0) : (spl - k0) / (k1 - k0);
         w = fmaf(tp, c1 - c0, c0);
     }
     return P * w;
 }
 
 template <int OP>
-__device__ __forceinline__ void apply_op(const StftArgs& a, const float* thr, float scale, int k, float& re, float& im) {
+__device__ __forceinline__ void apply_op(const StftArgs& a, const float* tbl, float scale, int k, float& re, float& im) {
     if (OP == OP_MASK) op_mask(a, k, re, im);
-    else if (OP == OP_PHON) op_phon(thr, k, re, im);
+    else if (OP == OP_PHON) op_phon(tbl, k, re, im);
+    else if (OP == OP_PHON_DB) op_phon_db(tbl, k, re, im);
     else if (OP == OP_SCALE) { re *= scale; im *= scale; }
 }
 
 // ---- the spectral middle of one frame -----------------------------------------------------------
 // Works on conjugate-symmetric pairs (k, N-k) of the half-length complex FFT held in `buf`:
 //   forward split  Z -> X[k], X[N-k]   |   op / store / reduce   |   inverse merge  X' -> Z' (scaled by 1/n_fft)
+// Lane l handles k = l + 32 i; k = 0 pairs DC with Nyquist (Z[N] = Z[0]); k = N/2 pairs with itself.
 template <int NFFT, int SRC, int SINK, int OP>
 __device__ __forceinline__ void spectral_middle(const StftArgs& a, float2* buf, const float2* __restrict__ post,
-                                                const float* thr, float scale, int lane, long long spec_off,
-                                                float& acc) {
+                                                const float* tbl, float scale, int lane, const LaneBase<NFFT>& lb,
+                                                long long spec_off, float& acc) {
     using P = Plan<NFFT>;
     constexpr int N = P::N;
     constexpr float inv_n = 1.f / (float)NFFT;
-    auto pair = [&](int k) {
+    // SELF: the k = N/2 bin, its own partner.
+    auto pair = [&](int k, int ia, int ib, auto self_tag) {
+        constexpr bool SELF = decltype(self_tag)::value;
         const int kn = N - k;                       // partner bin; for k == 0 this is the Nyquist bin N
         float2 X, Y;                                // X = X[k], Y = X[N-k]
         if (SRC == SRC_TIME) {
-            const float2 za = buf[P::swz(k)], zb = buf[P::swz(kn & (N - 1))];
+            const float2 za = buf[ia], zb = SELF ? za : buf[ib];
             const float2 w = post[k];               // (cos, sin) of 2 pi k / n_fft
             const float er = 0.5f * (za.x + zb.x), ei = 0.5f * (za.y - zb.y);
             const float o_r = 0.5f * (za.y + zb.y), o_i = -0.5f * (za.x - zb.x);
@@ -172,19 +201,19 @@ __device__ __forceinline__ void spectral_middle(const StftArgs& a, float2* buf, 
             Y = make_float2(er - tr, -(ei - ti));
         } else {
             X = a.spec_in[spec_off + (long long)k * a.sf];
-            Y = a.spec_in[spec_off + (long long)kn * a.sf];
+            Y = SELF ? X : a.spec_in[spec_off + (long long)kn * a.sf];
         }
         if (SINK == SINK_REDUCE) {
-            acc += fm_term(a, k, X.x, X.y);
-            if (kn != k) acc += fm_term(a, kn, Y.x, Y.y);
+            acc += fm_term<true>(a, k, X.x, X.y);
+            if (!SELF) acc += fm_term<true>(a, kn, Y.x, Y.y);
             return;
         }
-        apply_op<OP>(a, thr, scale, k, X.x, X.y);
-        if (kn != k) apply_op<OP>(a, thr, scale, kn, Y.x, Y.y);
+        apply_op<OP>(a, tbl, scale, k, X.x, X.y);
+        if (!SELF) apply_op<OP>(a, tbl, scale, kn, Y.x, Y.y);
         else Y = X;
         if (SINK == SINK_SPEC) {
             a.spec_out[spec_off + (long long)k * a.sf] = X;
-            if (kn != k) a.spec_out[spec_off + (long long)kn * a.sf] = Y;
+            if (!SELF) a.spec_out[spec_off + (long long)kn * a.sf] = Y;
             return;
         }
         // inverse merge; irfft ignores the imaginary parts of the DC and Nyquist bins
@@ -192,12 +221,16 @@ __device__ __forceinline__ void spectral_middle(const StftArgs& a, float2* buf, 
         const float2 w = post[k];
         const float ar = X.x + Y.x, ai = X.y - Y.y, br = X.x - Y.x, bi = X.y + Y.y;
         const float pr = w.x * br - w.y * bi, pi = w.x * bi + w.y * br;
-        buf[P::swz(k)] = make_float2(inv_n * (ar - pi), inv_n * (ai + pr));
-        if (k != 0) buf[P::swz(kn)] = make_float2(inv_n * (ar + pi), inv_n * (pr - ai));
+        buf[ia] = make_float2(inv_n * (ar - pi), inv_n * (ai + pr));
+        if (!SELF && k != 0) buf[ib] = make_float2(inv_n * (ar + pi), inv_n * (pr - ai));
     };
 #pragma unroll 2
-    for (int i = 0; i < N / 64; ++i) pair(lane + 32 * i);
-    if (lane == 0) pair(N / 2);
+    for (int i = 0; i < N / 64; ++i) {
+        const int k = lane + 32 * i;
+        const int kb = (N - k) & (N - 1);           // storage index of the partner (Z[N] aliases Z[0])
+        pair(k, lb.ld + padc(32 * i), padc(kb), std::false_type{});
+    }
+    if (lane == 0) pair(N / 2, padc(N / 2), padc(N / 2), std::true_type{});
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
@@ -219,13 +252,13 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     // shared-memory carve-up (all offsets multiples of 16 bytes)
     unsigned char* sp = smem;
     float* s_win = (float*)sp;
-    const float2* s_tw = (const float2*)(sp + a.off_tw);
+    const float4* s_tw = (const float4*)(sp + a.off_tw);
     const float2* s_post = (const float2*)(sp + a.off_post);
     sp += a.blob_bytes;
     float* s_thr = (float*)sp;
-    if (OP == OP_PHON) sp += ((F * 4 + 15) / 16) * 16;
+    if (OP == OP_PHON || OP == OP_PHON_DB) sp += ((F * 4 + 15) / 16) * 16;
     float2* s_fft = (float2*)sp;
-    sp += (size_t)kWarps * N * sizeof(float2);
+    sp += (size_t)kWarps * BufLayout<NFFT>::kFloat2 * sizeof(float2);
     float* s_in = (float*)sp;
     if (SRC == SRC_TIME) sp += (size_t)lin * 4;
     float* s_ola = (float*)sp;
@@ -284,7 +317,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     // ---- max_phon: scaled threshold  thr[k] = spl_thresh[k] - max(spl_thresh) + reference_db ------
     float scale = 1.f;
     if (OP == OP_SCALE) scale = a.scalars[PAA_S_SCALE];
-    if (OP == OP_PHON) {
+    if (OP == OP_PHON || OP == OP_PHON_DB) {
         float mx = -INFINITY;
         for (int k = tid; k < F; k += kThreadsStft) mx = fmaxf(mx, a.spl_thresh[k]);
 #pragma unroll
@@ -294,13 +327,18 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
         mx = red[0];
 #pragma unroll
         for (int w = 1; w < kWarps; ++w) mx = fmaxf(mx, red[w]);
-        for (int k = tid; k < F; k += kThreadsStft) s_thr[k] = (a.spl_thresh[k] - mx) + a.ref_db;
+        // OP_PHON keeps the limit as a magnitude, 10^(thr/20); OP_PHON_DB keeps it in dB
+        for (int k = tid; k < F; k += kThreadsStft) {
+            const float thr = (a.spl_thresh[k] - mx) + a.ref_db;
+            s_thr[k] = OP == OP_PHON ? exp10f(thr / 20.f) : thr;
+        }
     }
     mbar_wait(&bar, 0);
     __syncthreads();
 
     // ---- frames ----------------------------------------------------------------------------------
-    float2* buf = s_fft + (size_t)warp * N;
+    float2* buf = s_fft + (size_t)warp * BufLayout<NFFT>::kFloat2;
+    const LaneBase<NFFT> lb(lane);
     const float2* win2 = reinterpret_cast<const float2*>(s_win);
     float acc = 0.f;
     for (int r = 0; r < R; ++r) {
@@ -312,19 +350,19 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
             if (SRC == SRC_TIME) {
                 const float2* x2 = reinterpret_cast<const float2*>(s_in + f * hop);
                 fft_warp<NFFT, -1>(
-                    buf, s_tw, lane,
-                    [&](int m) { const float2 xv = x2[m], wv = win2[m]; return make_float2(xv.x * wv.x, xv.y * wv.y); },
-                    [&](int m, float2 v) { buf[P::swz(m)] = v; });
+                    buf, s_tw, lane, lb,
+                    [&](int m, int) { const float2 xv = x2[m], wv = win2[m]; return make_float2(xv.x * wv.x, xv.y * wv.y); },
+                    [&](int, int c, float2 v) { buf[lb.ld + padc(c)] = v; });
                 __syncwarp();
             }
-            spectral_middle<NFFT, SRC, SINK, OP>(a, buf, s_post, s_thr, scale, lane, spec_off, acc);
+            spectral_middle<NFFT, SRC, SINK, OP>(a, buf, s_post, s_thr, scale, lane, lb, spec_off, acc);
             if (SINK == SINK_TIME) {
                 __syncwarp();
                 const int obase = (f - R + 1) * hop;                 // owned-region coordinate of frame sample 0
                 const int olim = S * hop;
                 fft_warp<NFFT, +1>(
-                    buf, s_tw, lane, [&](int m) { return buf[P::swz(m)]; },
-                    [&](int m, float2 v) {
+                    buf, s_tw, lane, lb, [&](int, int c) { return buf[lb.ld + padc(c)]; },
+                    [&](int m, int, float2 v) {
                         const int o = obase + 2 * m;
                         if (o >= 0 && o < olim) {
                             const float2 wv = win2[m];
@@ -443,7 +481,7 @@ __global__ void k_spec_fm_partials(StftArgs a, int F) {
         if (a.sf <= a.st) { k = (int)(i % F); t = (int)((i / F) % a.n_frames); b = (int)(i / ((long long)F * a.n_frames)); }
         else { t = (int)(i % a.n_frames); k = (int)((i / a.n_frames) % F); b = (int)(i / ((long long)F * a.n_frames)); }
         const float2 X = a.spec_in[b * a.sb + k * a.sf + t * a.st];
-        acc += fm_term(a, k, X.x, X.y);
+        acc += fm_term<false>(a, k, X.x, X.y);
     }
     __shared__ float sh[32];
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -462,8 +500,8 @@ template <int NFFT>
 size_t smem_bytes(const paa_handle* h, int src, int sink, int op, int FT, int S) {
     constexpr int N = NFFT / 2;
     size_t b = h->blob_bytes;
-    if (op == OP_PHON) b += (((N + 1) * 4 + 15) / 16) * 16;
-    b += (size_t)kWarps * N * sizeof(float2);
+    if (op == OP_PHON || op == OP_PHON_DB) b += (((N + 1) * 4 + 15) / 16) * 16;
+    b += (size_t)kWarps * (N + N / 16) * sizeof(float2);
     if (src == SRC_TIME) b += (size_t)((FT - 1) * h->hop + NFFT) * 4;
     if (sink == SINK_TIME) b += (size_t)S * h->hop * 4;
     return b;
@@ -503,6 +541,16 @@ void fill_common(const paa_handle* h, StftArgs& a, int rows, int T, int n_frames
 }
 
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+// min_max_freqs: f_k = fp32(k)*fp32(bin_hz) compared in fp32 against fp32(min/max) like torch does
+// (projections.py:74-76); monotone in k, so two bin indices describe the mask exactly.
+void set_band(const paa_handle* h, StftArgs& a, double min_freq, double max_freq) {
+    a.f_min = (float)min_freq; a.f_max = (float)max_freq;
+    int lo = 0, hi = h->F;
+    while (lo < h->F && (float)lo * h->bin_hz < a.f_min) ++lo;            // bins [0, lo) are below the band
+    while (hi > 0 && (float)(hi - 1) * h->bin_hz > a.f_max) --hi;         // bins [hi, F) are above the band
+    a.k_lo = lo; a.k_hi = hi;
+}
 
 // torch.istft refuses windows whose overlap-add envelope (after trimming n_fft/2) falls below 1e-11
 bool nola_ok(const paa_handle* h, int n_frames) {
@@ -582,7 +630,7 @@ int paa_project_min_max_freqs(paa_handle* h, const float* p_in, float* p_out, in
     rc = prepare_source(h, p_in, rows, T, step, scratch, st, &src, &grad, &lr);
     if (rc) return rc;
     StftArgs a{};
-    a.f_min = (float)min_freq; a.f_max = (float)max_freq;
+    set_band(h, a, min_freq, max_freq);
     return run_fused<OP_MASK>(h, a, src, grad, lr, p_out, rows, T, out_len, st);
 }
 
@@ -686,7 +734,8 @@ int paa_spec_min_max_freqs(paa_handle* h, const float* spec_in, float* spec_out,
     StftArgs a{};
     fill_common(h, a, rows, 0, n_frames);
     a.spec_in = reinterpret_cast<const float2*>(spec_in); a.spec_out = reinterpret_cast<float2*>(spec_out);
-    a.sb = sb; a.sf = sf; a.st = stt; a.f_min = (float)min_freq; a.f_max = (float)max_freq;
+    a.sb = sb; a.sf = sf; a.st = stt;
+    set_band(h, a, min_freq, max_freq);
     k_spec_op<OP_MASK><<<spec_grid(h, (long long)rows * h->F * n_frames), 256, 0, (cudaStream_t)stream>>>(a, h->F, nullptr);
     PAA_LAUNCH_CHECK(h);
     return PAA_OK;
@@ -703,7 +752,7 @@ int paa_spec_phon_level(paa_handle* h, const float* spec_in, float* spec_out, in
     cudaStream_t st = (cudaStream_t)stream;
     k_thr_scaled<<<1, 256, 0, st>>>(spl_thresh_F, h->F, (float)phon_reference_db, h->d_thr_tmp);
     PAA_LAUNCH_CHECK(h);
-    k_spec_op<OP_PHON><<<spec_grid(h, (long long)rows * h->F * n_frames), 256, 0, st>>>(a, h->F, h->d_thr_tmp);
+    k_spec_op<OP_PHON_DB><<<spec_grid(h, (long long)rows * h->F * n_frames), 256, 0, st>>>(a, h->F, h->d_thr_tmp);
     PAA_LAUNCH_CHECK(h);
     return PAA_OK;
 }

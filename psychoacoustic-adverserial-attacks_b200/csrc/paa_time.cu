@@ -76,9 +76,9 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     return v;
 }
-template <int NQ>
+template <int NQ, int NT = kThreads>
 __device__ __forceinline__ void block_sum(double (&acc)[NQ], double* out /* [NQ] or nullptr */) {
-    __shared__ double sh[NQ][kThreads / 32];
+    __shared__ double sh[NQ][NT / 32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
@@ -89,7 +89,7 @@ __device__ __forceinline__ void block_sum(double (&acc)[NQ], double* out /* [NQ]
     if (w == 0) {
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            double s = lane < kThreads / 32 ? sh[q][lane] : 0.0;
+            double s = lane < NT / 32 ? sh[q][lane] : 0.0;
             s = warp_sum(s);
             if (lane == 0 && out) out[q] = s;
         }
@@ -237,6 +237,32 @@ struct FinalArgs {
     double n_clean;      // numel(clean)
 };
 
+// The reference's data-dependent branch, in its fp32 arithmetic, from the two global sums.
+template <int NORM>
+__device__ __forceinline__ void final_math(double tot0, double tot1, const FinalArgs& a, float& scale, float& norm,
+                                           float& aux0, float& aux1) {
+    scale = 1.f; norm = 0.f; aux0 = 0.f; aux1 = 0.f;
+    if (NORM == NORM_L2) {                                   // projections.py:41-46
+        norm = sqrtf((float)tot0);
+        if (norm > a.eps) scale = __frcp_rn(norm) * a.eps;     // python `eps / tensor` = reciprocal()*eps
+    } else if (NORM == NORM_SNR) {                           // projections.py:11-35
+        const float p_noise = (float)(tot0 / a.n_p);
+        const float p_sig = (float)(tot1 / a.n_clean);
+        aux0 = p_sig;
+        aux1 = 10.f * log10f(p_sig / (p_noise + 1e-12f));
+        norm = sqrtf((float)tot0);
+        if (!(aux1 >= a.eps) && !(norm < 1e-8f)) {
+            const float want = sqrtf((p_sig / (float)a.snr_linear) * (float)a.n_clean);
+            scale = want / norm;
+        }
+    } else {                                                 // projections.py:56-66
+        norm = (float)tot0;
+        aux0 = (float)tot1;
+        aux1 = a.eps * aux0;
+        if (norm > aux1) scale = aux1 / norm;
+    }
+}
+
 template <int NORM>
 __global__ void __launch_bounds__(kThreads) k_finalize(FinalArgs a) {
     double acc[2] = {0.0, 0.0};
@@ -248,26 +274,8 @@ __global__ void __launch_bounds__(kThreads) k_finalize(FinalArgs a) {
     block_sum<2>(acc, tot);
     __syncthreads();
     if (threadIdx.x != 0) return;
-    float scale = 1.f, norm = 0.f, aux0 = 0.f, aux1 = 0.f;
-    if (NORM == NORM_L2) {                                   // projections.py:41-46
-        norm = sqrtf((float)tot[0]);
-        if (norm > a.eps) scale = __frcp_rn(norm) * a.eps;     // python `eps / tensor` = reciprocal()*eps
-    } else if (NORM == NORM_SNR) {                           // projections.py:11-35
-        const float p_noise = (float)(tot[0] / a.n_p);
-        const float p_sig = (float)(tot[1] / a.n_clean);
-        aux0 = p_sig;
-        aux1 = 10.f * log10f(p_sig / (p_noise + 1e-12f));
-        norm = sqrtf((float)tot[0]);
-        if (!(aux1 >= a.eps) && !(norm < 1e-8f)) {
-            const float want = sqrtf((p_sig / (float)a.snr_linear) * (float)a.n_clean);
-            scale = want / norm;
-        }
-    } else {                                                 // projections.py:56-66
-        norm = (float)tot[0];
-        aux0 = (float)tot[1];
-        aux1 = a.eps * aux0;
-        if (norm > aux1) scale = aux1 / norm;
-    }
+    float scale, norm, aux0, aux1;
+    final_math<NORM>(tot[0], tot[1], a, scale, norm, aux0, aux1);
     a.scalars[PAA_S_SCALE] = scale;
     a.scalars[PAA_S_NORM] = norm;
     a.scalars[PAA_S_AUX0] = aux0;
@@ -292,6 +300,138 @@ __global__ void __launch_bounds__(kThreads) k_scale(const float* q_in, float* p_
     } else {
         for (int64_t i = tid; i < n; i += nth) p_out[i] = q_in[i] * sc;
     }
+}
+
+// ---- kernel: the whole reducing projection in ONE cooperative launch ----------------------------
+// Phase A (step + reduce) -> grid barrier -> every block re-sums the partials in the same fixed
+// order -> phase B (rescale).  Each thread revisits exactly the float4s it produced in phase A, and
+// keeps the first kRC of them in registers and the next `sc_iters` in shared memory across the
+// barrier, so up to (kRC + sc_iters) * 4 * gridDim.x * kFT elements (~12 M on a B200) never make
+// the q round trip through HBM: 12 B/element of traffic instead of the 20 B the two-pass form needs.
+constexpr int kFT = 512;
+constexpr int kRC = 4;
+constexpr int kSCMax = 12;
+
+template <int NORM, int STEP>
+__global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, FinalArgs f, int sc_iters) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ float4 cache[];                       // [sc_iters][kFT]
+    const int64_t tid = (int64_t)blockIdx.x * kFT + threadIdx.x, nth = (int64_t)gridDim.x * kFT;
+    const int64_t n4 = a.n >> 2;
+    float acc0 = 0.f, acc1 = 0.f;
+    float4 keep[kRC];
+
+    auto phase_a = [&](int64_t i4) -> float4 {
+        const int64_t i = i4 * 4;
+        if (NORM != NORM_TV) {
+            const float4 x = stepped4<STEP, true>(a.p_in, i, s);
+            acc0 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+            return x;
+        } else {
+            const float4 x = stepped4<STEP, false>(a.p_in, i, s);
+            const float nx = (i + 4 < a.n) ? stepped1<STEP, false>(a.p_in, i + 4, s) : 0.f;
+            const int c = (int)(i % a.T), Tp = a.T;
+            float t = 0.f;
+            if (c != Tp - 1) t += fabsf(x.y - x.x);
+            if ((c + 1) % Tp != Tp - 1) t += fabsf(x.z - x.y);
+            if ((c + 2) % Tp != Tp - 1) t += fabsf(x.w - x.z);
+            if ((c + 3) % Tp != Tp - 1 && i + 4 < a.n) t += fabsf(nx - x.w);
+            acc0 += t;
+            return x;
+        }
+    };
+
+#pragma unroll
+    for (int k = 0; k < kRC; ++k) {
+        const int64_t i4 = tid + k * nth;
+        if (i4 < n4) keep[k] = phase_a(i4);
+    }
+    {
+        int k = kRC;
+        for (int64_t i4 = tid + kRC * nth; i4 < n4; i4 += nth, ++k) {
+            const float4 x = phase_a(i4);
+            if (k < kRC + sc_iters) cache[(k - kRC) * kFT + threadIdx.x] = x;
+            else if (a.write_q) st4(a.q_out + i4 * 4, x);
+        }
+    }
+    if (tid == 0) {                                         // the n % 4 trailing elements go through global memory
+        for (int64_t i = n4 << 2; i < a.n; ++i) {
+            const float x = stepped1<STEP, NORM != NORM_TV>(a.p_in, i, s);
+            a.q_out[i] = x;
+            if (NORM != NORM_TV) acc0 += x * x;
+            else if ((int)(i % a.T) != a.T - 1 && i + 1 < a.n) acc0 += fabsf(stepped1<STEP, false>(a.p_in, i + 1, s) - x);
+        }
+    }
+    if (NORM == NORM_SNR) {
+        const int64_t c4 = a.clean_n >> 2;
+        for (int64_t i = tid; i < c4; i += nth) {
+            const float4 c = ld4_stream(a.clean + i * 4);
+            acc1 += (c.x * c.x + c.y * c.y) + (c.z * c.z + c.w * c.w);
+        }
+        for (int64_t i = (c4 << 2) + tid; i < a.clean_n; i += nth) { const float c = a.clean[i]; acc1 += c * c; }
+    } else if (NORM == NORM_TV) {
+        const int64_t c4 = a.clean_n >> 2;
+        const int Tc = a.clean_T;
+        for (int64_t i4 = tid; i4 < c4; i4 += nth) {
+            const int64_t i = i4 * 4;
+            const float4 x = ld4_stream(a.clean + i);
+            const float nx = (i + 4 < a.clean_n) ? a.clean[i + 4] : 0.f;
+            const int c = (int)(i % Tc);
+            float t = 0.f;
+            if (c != Tc - 1) t += fabsf(x.y - x.x);
+            if ((c + 1) % Tc != Tc - 1) t += fabsf(x.z - x.y);
+            if ((c + 2) % Tc != Tc - 1) t += fabsf(x.w - x.z);
+            if ((c + 3) % Tc != Tc - 1 && i + 4 < a.clean_n) t += fabsf(nx - x.w);
+            acc1 += t;
+        }
+        for (int64_t i = (c4 << 2) + tid; i < a.clean_n; i += nth)
+            if ((int)(i % Tc) != Tc - 1 && i + 1 < a.clean_n) acc1 += fabsf(a.clean[i + 1] - a.clean[i]);
+    }
+    double wide[2] = {(double)acc0, (double)acc1};
+    block_sum<2, kFT>(wide, a.partials + 2 * (int64_t)blockIdx.x);
+    __threadfence();
+    grid.sync();
+
+    // every block sums the same partials in the same order: identical scale everywhere, no second barrier
+    double part[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kFT) {
+        part[0] += a.partials[2 * i];
+        part[1] += a.partials[2 * i + 1];
+    }
+    __shared__ double tot[2];
+    __shared__ float s_scale;
+    block_sum<2, kFT>(part, tot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float scale, norm, aux0, aux1;
+        final_math<NORM>(tot[0], tot[1], f, scale, norm, aux0, aux1);
+        s_scale = scale;
+        if (blockIdx.x == 0) {
+            f.scalars[PAA_S_SCALE] = scale;
+            f.scalars[PAA_S_NORM] = norm;
+            f.scalars[PAA_S_AUX0] = aux0;
+            f.scalars[PAA_S_AUX1] = aux1;
+        }
+    }
+    __syncthreads();
+    const float sc = s_scale;
+    if (sc == 1.f && !a.write_q) return;                    // in place and already feasible: nothing to store
+
+    auto scaled = [sc](float4 x) { x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; return x; };
+#pragma unroll
+    for (int k = 0; k < kRC; ++k) {
+        const int64_t i4 = tid + k * nth;
+        if (i4 < n4) st4(a.q_out + i4 * 4, scaled(keep[k]));
+    }
+    {
+        int k = kRC;
+        for (int64_t i4 = tid + kRC * nth; i4 < n4; i4 += nth, ++k) {
+            if (k < kRC + sc_iters) st4(a.q_out + i4 * 4, scaled(cache[(k - kRC) * kFT + threadIdx.x]));
+            else if (sc != 1.f) st4(a.q_out + i4 * 4, scaled(ld4(a.q_out + i4 * 4)));
+        }
+    }
+    if (tid == 0 && sc != 1.f)
+        for (int64_t i = n4 << 2; i < a.n; ++i) a.q_out[i] *= sc;
 }
 
 // ---- kernel: compose + clamp (train.py:136): x_adv[b,t] = clamp(clean[b,t] + p[b % p_rows, t]) --
@@ -374,6 +514,34 @@ int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int
                (mode == PAA_STEP_NONE || aligned16(sd.grad)) &&
                (mode != PAA_STEP_ADAM || (aligned16(sd.m) && aligned16(sd.v)));
     int64_t work = std::max<int64_t>(n, a.clean_n);
+    FinalArgs f{};
+    f.partials = a.partials; f.scalars = scratch_scalars(scratch);
+    f.eps = eps; f.snr_linear = snr_linear; f.n_p = (double)n; f.n_clean = (double)clean_n;
+    if (vec && !h->no_coop) {
+        // single cooperative launch; fall through to the three-kernel form only if the device refuses it
+        void* kern = nullptr;
+        switch (mode) {
+            case PAA_STEP_NONE: kern = (void*)k_fused<NORM, PAA_STEP_NONE>; break;
+            case PAA_STEP_PGD: kern = (void*)k_fused<NORM, PAA_STEP_PGD>; break;
+            default: kern = (void*)k_fused<NORM, PAA_STEP_ADAM>; break;
+        }
+        const int max_grid = 2 * h->num_sms;
+        const int64_t work4 = (work + 3) / 4;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, (work4 + kFT - 1) / kFT));
+        const int64_t iters = ((n >> 2) + (int64_t)grid * kFT - 1) / ((int64_t)grid * kFT);
+        int sc_iters = (int)std::max<int64_t>(0, std::min<int64_t>(kSCMax, iters - kRC));
+        size_t smem = (size_t)sc_iters * kFT * sizeof(float4);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSCMax * kFT * sizeof(float4)));
+        f.nblocks = grid;
+        void* params[] = {(void*)&a, (void*)&sd, (void*)&f, (void*)&sc_iters};
+        if (e == cudaSuccess) e = cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kFT), params, smem, st);
+        if (e == cudaSuccess) {
+            __atomic_add_fetch(&g_paa_launches, 1, __ATOMIC_RELAXED);
+            return PAA_OK;
+        }
+        (void)cudaGetLastError();
+        h->no_coop = 1;
+    }
     int grid = std::min(grid_for(h, vec ? (work + 3) / 4 : work), kMaxPartialBlocks);
     switch (mode) {
         case PAA_STEP_NONE: rc = launch_reduce<NORM, PAA_STEP_NONE>(h, a, sd, grid, vec, st); break;
@@ -381,9 +549,7 @@ int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int
         default: rc = launch_reduce<NORM, PAA_STEP_ADAM>(h, a, sd, grid, vec, st); break;
     }
     if (rc) return rc;
-    FinalArgs f{};
-    f.partials = a.partials; f.nblocks = grid; f.scalars = scratch_scalars(scratch);
-    f.eps = eps; f.snr_linear = snr_linear; f.n_p = (double)n; f.n_clean = (double)clean_n;
+    f.nblocks = grid;
     k_finalize<NORM><<<1, kThreads, 0, st>>>(f);
     PAA_LAUNCH_CHECK(h);
     bool vb = aligned16(p_out);

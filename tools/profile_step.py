@@ -55,6 +55,7 @@ for norm in a.norms.split(","):
     args.device = str(dev)
     thr = pbuild.init_phon_threshold_tensor(args)
     for r in range(a.reps + 1):
+        torch.cuda._sleep(400_000)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         paa_b200.step_and_project(p, grad, clean, args, interp, thr)
