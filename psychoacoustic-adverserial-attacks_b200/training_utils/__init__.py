@@ -1,1 +1,1 @@
-from . import build, parser, train  # noqa: F401
+from . import build, parser, sharding, train  # noqa: F401
