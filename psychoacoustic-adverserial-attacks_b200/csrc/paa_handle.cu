@@ -78,7 +78,11 @@ int paa_create(int device, int n_fft, int hop, int sr, paa_handle** out) {
     h->off_post = round16(h->off_twiddle + tw.size() * 4);
     h->blob_bytes = round16(h->off_post + post.size() * 4);
     std::vector<unsigned char> blob(h->blob_bytes, 0);
-    std::memcpy(blob.data(), h->h_window.data(), (size_t)n_fft * 4);
+    {   // the device table holds w/2 (exact): the real-FFT split then needs no 0.5, and 2/n_fft is folded into the per-bin op
+        std::vector<float> half(h->h_window);
+        for (float& v : half) v *= 0.5f;
+        std::memcpy(blob.data(), half.data(), (size_t)n_fft * 4);
+    }
     std::memcpy(blob.data() + h->off_twiddle, tw.data(), tw.size() * 4);
     std::memcpy(blob.data() + h->off_post, post.data(), post.size() * 4);
     e = cudaMalloc(&h->d_blob, h->blob_bytes);

@@ -98,8 +98,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
 // project_min_max_freqs (projections.py:74-79): keep f < f_min or f > f_max, zero the band between.
 // f_k = fp32(k) * fp32(bin_hz) is monotone in k, so the host turns the two float comparisons into
 // bin indices (keep k < k_lo or k >= k_hi) with the same fp32 arithmetic.
-__device__ __forceinline__ void op_mask(const StftArgs& a, int k, float& re, float& im) {
-    const float keep = (k < a.k_lo || k >= a.k_hi) ? 1.f : 0.f;
+template <bool SCALED>
+__device__ __forceinline__ void op_mask(const StftArgs& a, int k, float c, float& re, float& im) {
+    const float keep = (k < a.k_lo || k >= a.k_hi) ? (SCALED ? c : 1.f) : 0.f;
     re *= keep;
     im *= keep;
 }
@@ -125,22 +126,35 @@ __device__ __forceinline__ void op_phon_db(const float* thr, int k, float& re, f
 // The same projection in the linear domain, used by the fused kernel: with lim[k] = 10^(thr[k]/20),
 //   |X'| = min(|X| + 1e-8, lim[k])   -- the dB round trip is the identity on un-clipped bins up to
 // fp32 rounding (~1e-6 relative, inside the 1e-5 parity bar) and log10 is monotone, so no log/exp per bin.
-__device__ __forceinline__ void op_phon(const float* lim, int k, float& re, float& im) {
-    const float m = sqrtf(fmaf(re, re, im * im));
-    const float x = m + 1e-8f;
-    const float l = lim[k];
-    const float mag = (x > l) ? l : x;              // NaN falls through like torch.where(db > thr, ...)
-    if (m > 1e-18f) {
-        const float g = __fdividef(mag, m);
-        re *= g;
-        im *= g;
-    } else {
-        const float ph = atan2f(im, re);
-        float s, c;
-        sincosf(ph, &s, &c);
-        re = mag * c;
-        im = mag * s;
+// `c` is the power-of-two factor 2/n_fft the inverse transform wants folded in; lim_c[k] = c * lim[k].
+// One MUFU.RSQ gives both |X| = P * rsqrt(P) and the unit phasor X * rsqrt(P).
+__device__ __forceinline__ void op_phon(const float* lim_c, int k, float c, float& re, float& im) {
+    const float P = fmaf(re, re, im * im);
+    const float r = rsqrtf(P);
+    const float l = lim_c[k];
+    if (__builtin_expect(__any_sync(0xffffffffu, !(P > 1e-36f)) != 0, 0)) {
+        // some lane has a zero / denormal-magnitude bin: exact magnitude, phase from atan2 like torch.angle
+        const float m = sqrtf(P);
+        const float xc = fmaf(m, c, 1e-8f * c);
+        const float mag = (xc > l) ? l : xc;
+        if (P > 1e-36f) {
+            const float g = mag * r;
+            re *= g;
+            im *= g;
+        } else {
+            const float ph = atan2f(im, re);
+            float sn, cs;
+            sincosf(ph, &sn, &cs);
+            re = mag * cs;
+            im = mag * sn;
+        }
+        return;
     }
+    const float xc = fmaf(P * r, c, 1e-8f * c);       // c * (|X| + 1e-8)
+    const float mag = (xc > l) ? l : xc;              // NaN falls through like torch.where(db > thr, ...)
+    const float g = mag * r;
+    re *= g;
+    im *= g;
 }
 // compute_fm_weighted_norm_interp (projections.py:93-113): P * w(10 log10(P+1e-10), f_k)
 template <bool FAST>
@@ -167,12 +181,16 @@ __device__ __forceinline__ float fm_term(const StftArgs& a, int k, float re, flo
     return P * w;
 }
 
-template <int OP>
-__device__ __forceinline__ void apply_op(const StftArgs& a, const float* tbl, float scale, int k, float& re, float& im) {
-    if (OP == OP_MASK) op_mask(a, k, re, im);
-    else if (OP == OP_PHON) op_phon(tbl, k, re, im);
+// SCALED: the fused kernel folds the inverse transform's power-of-two factor c = 2/n_fft into the operator
+// (the forward window table holds w/2, so c * w/2 = w/n_fft); the element-wise spectrum kernels do not.
+template <int OP, bool SCALED>
+__device__ __forceinline__ void apply_op(const StftArgs& a, const float* tbl, float scale, float c, int k, float& re,
+                                         float& im) {
+    if (OP == OP_MASK) op_mask<SCALED>(a, k, c, re, im);
+    else if (OP == OP_PHON) op_phon(tbl, k, SCALED ? c : 1.f, re, im);
     else if (OP == OP_PHON_DB) op_phon_db(tbl, k, re, im);
-    else if (OP == OP_SCALE) { re *= scale; im *= scale; }
+    else if (OP == OP_SCALE) { re *= scale; im *= scale; }          // caller pre-multiplies scale by c
+    else if (SCALED) { re *= c; im *= c; }
 }
 
 // ---- the spectral middle of one frame -----------------------------------------------------------
@@ -185,17 +203,19 @@ __device__ __forceinline__ void spectral_middle(const StftArgs& a, float2* buf, 
                                                 long long spec_off, float& acc) {
     using P = Plan<NFFT>;
     constexpr int N = P::N;
-    constexpr float inv_n = 1.f / (float)NFFT;
+    constexpr float kC = 2.f / (float)NFFT;      // see apply_op: folded into the operator on the way to the inverse
+    constexpr bool TO_TIME = SINK == SINK_TIME;
     // SELF: the k = N/2 bin, its own partner.
-    auto pair = [&](int k, int ia, int ib, auto self_tag) {
+    auto pair = [&](int k, int ia, int ib, auto self_tag, bool commit) {
         constexpr bool SELF = decltype(self_tag)::value;
         const int kn = N - k;                       // partner bin; for k == 0 this is the Nyquist bin N
         float2 X, Y;                                // X = X[k], Y = X[N-k]
         if (SRC == SRC_TIME) {
             const float2 za = buf[ia], zb = SELF ? za : buf[ib];
             const float2 w = post[k];               // (cos, sin) of 2 pi k / n_fft
-            const float er = 0.5f * (za.x + zb.x), ei = 0.5f * (za.y - zb.y);
-            const float o_r = 0.5f * (za.y + zb.y), o_i = -0.5f * (za.x - zb.x);
+            // the forward window table holds w/2, so Z is already halved: E = za + conj(zb), O = (za - conj(zb)) / i
+            const float er = za.x + zb.x, ei = za.y - zb.y;
+            const float o_r = za.y + zb.y, o_i = zb.x - za.x;
             const float tr = w.x * o_r + w.y * o_i, ti = w.x * o_i - w.y * o_r;
             X = make_float2(er + tr, ei + ti);
             Y = make_float2(er - tr, -(ei - ti));
@@ -204,15 +224,16 @@ __device__ __forceinline__ void spectral_middle(const StftArgs& a, float2* buf, 
             Y = SELF ? X : a.spec_in[spec_off + (long long)kn * a.sf];
         }
         if (SINK == SINK_REDUCE) {
-            acc += fm_term<true>(a, k, X.x, X.y);
+            const float t0 = fm_term<true>(a, k, X.x, X.y);
+            if (commit) acc += t0;
             if (!SELF) acc += fm_term<true>(a, kn, Y.x, Y.y);
             return;
         }
-        apply_op<OP>(a, tbl, scale, k, X.x, X.y);
-        if (!SELF) apply_op<OP>(a, tbl, scale, kn, Y.x, Y.y);
+        apply_op<OP, TO_TIME>(a, tbl, scale, kC, k, X.x, X.y);
+        if (!SELF) apply_op<OP, TO_TIME>(a, tbl, scale, kC, kn, Y.x, Y.y);
         else Y = X;
         if (SINK == SINK_SPEC) {
-            a.spec_out[spec_off + (long long)k * a.sf] = X;
+            if (commit) a.spec_out[spec_off + (long long)k * a.sf] = X;
             if (!SELF) a.spec_out[spec_off + (long long)kn * a.sf] = Y;
             return;
         }
@@ -221,16 +242,17 @@ __device__ __forceinline__ void spectral_middle(const StftArgs& a, float2* buf, 
         const float2 w = post[k];
         const float ar = X.x + Y.x, ai = X.y - Y.y, br = X.x - Y.x, bi = X.y + Y.y;
         const float pr = w.x * br - w.y * bi, pi = w.x * bi + w.y * br;
-        buf[ia] = make_float2(inv_n * (ar - pi), inv_n * (ai + pr));
-        if (!SELF && k != 0) buf[ib] = make_float2(inv_n * (ar + pi), inv_n * (pr - ai));
+        if (commit) buf[ia] = make_float2(ar - pi, ai + pr);
+        if (!SELF && k != 0) buf[ib] = make_float2(ar + pi, pr - ai);
     };
 #pragma unroll 2
     for (int i = 0; i < N / 64; ++i) {
         const int k = lane + 32 * i;
         const int kb = (N - k) & (N - 1);           // storage index of the partner (Z[N] aliases Z[0])
-        pair(k, lb.ld + padc(32 * i), padc(kb), std::false_type{});
+        pair(k, lb.ld + padc(32 * i), padc(kb), std::false_type{}, true);
     }
-    if (lane == 0) pair(N / 2, padc(N / 2), padc(N / 2), std::true_type{});
+    // the self-paired bin: every lane computes it (the per-bin operators use warp votes), lane 0 commits
+    pair(N / 2, padc(N / 2), padc(N / 2), std::true_type{}, lane == 0);
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
@@ -316,7 +338,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
 
     // ---- max_phon: scaled threshold  thr[k] = spl_thresh[k] - max(spl_thresh) + reference_db ------
     float scale = 1.f;
-    if (OP == OP_SCALE) scale = a.scalars[PAA_S_SCALE];
+    if (OP == OP_SCALE) scale = a.scalars[PAA_S_SCALE] * (2.f / (float)NFFT);
     if (OP == OP_PHON || OP == OP_PHON_DB) {
         float mx = -INFINITY;
         for (int k = tid; k < F; k += kThreadsStft) mx = fmaxf(mx, a.spl_thresh[k]);
@@ -330,7 +352,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
         // OP_PHON keeps the limit as a magnitude, 10^(thr/20); OP_PHON_DB keeps it in dB
         for (int k = tid; k < F; k += kThreadsStft) {
             const float thr = (a.spl_thresh[k] - mx) + a.ref_db;
-            s_thr[k] = OP == OP_PHON ? exp10f(thr / 20.f) : thr;
+            s_thr[k] = OP == OP_PHON ? exp10f(thr / 20.f) * (2.f / (float)NFFT) : thr;
         }
     }
     mbar_wait(&bar, 0);
@@ -380,24 +402,53 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
 
     // ---- epilogue -----------------------------------------------------------------------------------
     if (SINK == SINK_TIME) {
-        // y[n] = ola[n] / sum_t w^2[n + n/2 - t*hop]  (torch.istft's window envelope), zero past hop*(T'-1)
+        // y[n] = ola[n] / sum_t w^2[n + n/2 - t*hop]  (torch.istft's window envelope), zero past hop*(T'-1).
+        // Interior hop-blocks share one reciprocal envelope table, built in the now idle FFT buffers; the
+        // R-1 blocks at either end of a row see fewer frames and take the slow path.
+        float* s_renv = reinterpret_cast<float*>(s_fft);
+        for (int q = tid; q < hop; q += kThreadsStft) {
+            float e = 0.f;
+            for (int d = R - 1; d >= 0; --d) { const float wv = 2.f * s_win[d * hop + q]; e += wv * wv; }
+            s_renv[q] = 1.f / e;
+        }
+        __syncthreads();
         float* yr = a.y + (size_t)row * a.out_len;
-        const int n_lo = ti * S * hop;
-        const int valid = hop * (a.n_frames - 1);
-        for (int o = tid; o < S * hop; o += kThreadsStft) {
-            const int n = n_lo + o;
-            if (n >= a.out_len) break;
-            float out = 0.f;
-            if (n < valid) {
-                const int u = n + NFFT / 2, ub = u / hop, qq = u - ub * hop;
-                float env = 0.f;
-                for (int d = R - 1; d >= 0; --d) {
-                    const int t = ub - d;
-                    if (t >= 0 && t < a.n_frames) { const float wv = s_win[d * hop + qq]; env += wv * wv; }
+        const bool vec = (a.out_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15u) == 0);
+        for (int jb = warp; jb < S; jb += kWarps) {
+            const int gb = ti * S + jb, n0 = gb * hop;
+            if (n0 >= a.out_len) break;                                   // warp-uniform
+            const int ub = gb + R / 2;                                    // newest frame covering this block
+            const bool exists = gb < a.n_frames - 1;
+            const bool interior = ub - R + 1 >= 0 && ub <= a.n_frames - 1;
+            for (int q = lane * 4; q < hop; q += 128) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (exists) {
+                    const float4 o = *reinterpret_cast<const float4*>(s_ola + jb * hop + q);
+                    float4 r;
+                    if (interior) {
+                        r = *reinterpret_cast<const float4*>(s_renv + q);
+                    } else {
+                        float e[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int d = R - 1; d >= 0; --d) {
+                            const int t = ub - d;
+                            if (t < 0 || t >= a.n_frames) continue;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) { const float wv = 2.f * s_win[d * hop + q + c]; e[c] += wv * wv; }
+                        }
+                        r = make_float4(1.f / e[0], 1.f / e[1], 1.f / e[2], 1.f / e[3]);
+                    }
+                    v = make_float4(o.x * r.x, o.y * r.y, o.z * r.z, o.w * r.w);
                 }
-                out = s_ola[o] / env;
+                const int n = n0 + q;
+                if (vec && n + 3 < a.out_len) {
+                    *reinterpret_cast<float4*>(yr + n) = v;
+                } else {
+                    if (n < a.out_len) yr[n] = v.x;
+                    if (n + 1 < a.out_len) yr[n + 1] = v.y;
+                    if (n + 2 < a.out_len) yr[n + 2] = v.z;
+                    if (n + 3 < a.out_len) yr[n + 3] = v.w;
+                }
             }
-            yr[n] = out;
         }
     } else if (SINK == SINK_REDUCE) {
 #pragma unroll
@@ -458,7 +509,7 @@ __global__ void k_spec_op(StftArgs a, int F, const float* thr_scaled) {
         else { t = (int)(i % a.n_frames); k = (int)((i / a.n_frames) % F); b = (int)(i / ((long long)F * a.n_frames)); }
         const long long off = b * a.sb + k * a.sf + t * a.st;
         float2 X = a.spec_in[off];
-        apply_op<OP>(a, thr_scaled, scale, k, X.x, X.y);
+        apply_op<OP, false>(a, thr_scaled, scale, 1.f, k, X.x, X.y);
         a.spec_out[off] = X;
     }
 }
