@@ -1,5 +1,6 @@
 // Handle life cycle of libpaa.so: immutable device tables for one (device, n_fft, hop, sr).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "paa_fft.cuh"
