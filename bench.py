@@ -275,10 +275,11 @@ def projection_sweep(dev, iters: int = 20):
     interp = iso.build_weight_interpolator()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     cases = [("linf", 4, 5, 1e-3, 12), ("snr", 32, 10, 0.01, 24), ("fletcher_munson", 64, 15, 0.1, 20),
-             ("max_phon", 64, 15, 0.03, 12), ("tv", 128, 10, 0.01, 24), ("min_max_freqs", 128, 10, 0.01, 12),
-             ("l2", 512, 10, 0.01, 20)]
+             ("fletcher_munson+identity", 64, 15, 0.1, 20), ("max_phon", 64, 15, 0.03, 12), ("tv", 128, 10, 0.01, 24),
+             ("min_max_freqs", 128, 10, 0.01, 12), ("l2", 512, 10, 0.01, 20)]
     out = {}
-    for norm, B, sec, sigma, bpe in cases:
+    for name, B, sec, sigma, bpe in cases:
+        norm = name.split("+")[0]
         T = sec * SR
         g = torch.Generator(device=dev).manual_seed(1234)
         clean = (torch.rand(B, T, generator=g, device=dev) * 2 - 1) * 0.1
@@ -286,6 +287,8 @@ def projection_sweep(dev, iters: int = 20):
         grad = torch.randn(B, T, generator=g, device=dev)
         args = pparser.create_arg_parser().parse_args(["--norm_type", norm, "--optimizer_type", "pgd", "--snr_db", "40"])
         args.device = str(dev)
+        # "+identity": pass B of fletcher_munson as s*q (ISTFT(s*STFT(q)) = s*q) instead of the literal round trip
+        args.fm_identity_roundtrip = name.endswith("+identity")
         thr = pbuild.init_phon_threshold_tensor(args)
         for _ in range(3):
             paa_b200.step_and_project(p, grad, clean, args, interp, thr)
@@ -301,9 +304,31 @@ def projection_sweep(dev, iters: int = 20):
             times.append(e0.elapsed_time(e1))
         ms = statistics.median(times)
         gbs = bpe * B * T / (ms * 1e-3) / 1e9
-        out[norm] = {"shape": f"{B}x{sec}s", "bytes_per_elem": bpe, "ms": round(ms, 4), "GB/s": round(gbs, 1),
+        out[name] = {"shape": f"{B}x{sec}s", "bytes_per_elem": bpe, "ms": round(ms, 4), "GB/s": round(gbs, 1),
                      "frac_of_measured_peak": round(gbs / peak, 4), "audio_s_per_s": round(B * sec / (ms * 1e-3), 1)}
+        # the kernel-for-kernel bar: the same torch ops the reference runs, eager, on this GPU
+        # (the oracle port; baseline leg only).  fletcher_munson includes its D2H -> host bilinear -> H2D trip.
+        try:
+            from oracle import paa_oracle as orc
+            hp = orc.Hyper(norm_type=norm, optimizer_type="pgd", snr_db=SNR_DB)
+            it_cpu = orc.build_weight_interpolator()
+            reps = 2 if norm == "fletcher_munson" else 5
+            want = orc.step_and_constrain(p, grad, clean, hp, it_cpu, thr)
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            for _ in range(reps):
+                orc.step_and_constrain(p, grad, clean, hp, it_cpu, thr)
+            torch.cuda.synchronize()
+            eager_ms = (time.perf_counter() - w0) * 1e3 / reps
+            got = paa_b200.step_and_project(p, grad, clean, args, interp, thr)
+            out[name]["torch_eager_ms"] = round(eager_ms, 3)
+            out[name]["speedup_vs_torch_eager"] = round(eager_ms / ms, 1)
+            out[name]["max_rel_err_vs_torch_eager"] = float(f"{float((got - want).abs().max() / want.abs().max()):.2e}")
+            del want, got
+        except Exception as exc:                                  # the comparator must never break the bench line
+            out[name]["torch_eager_ms"] = f"unavailable: {type(exc).__name__}"
         del clean, p, grad
+        torch.cuda.empty_cache()
     return out
 
 

@@ -190,7 +190,7 @@ def stft(x: torch.Tensor, n_fft: int, hop: int) -> torch.Tensor:
     half = n_fft // 2
     xp = torch.nn.functional.pad(x.unsqueeze(1), (half, half), mode="reflect").squeeze(1)
     frames = xp.unfold(-1, n_fft, hop)                           # (B, T', n_fft)
-    spec = torch.fft.rfft(frames * hann_periodic(n_fft), dim=-1)  # (B, T', F)
+    spec = torch.fft.rfft(frames * hann_periodic(n_fft).to(x.device), dim=-1)  # (B, T', F); window H2D as fourier_transforms.py:20
     return spec.transpose(1, 2)
 
 
@@ -198,7 +198,7 @@ def istft(spec: torch.Tensor, n_fft: int, hop: int) -> torch.Tensor:
     """Inverse of :func:`stft`: irfft, x window, overlap-add, / sum(window^2), trim n_fft/2.
     (B,F,T') -> (B, hop*(T'-1))."""
     B, _, n_frames = spec.shape
-    w = hann_periodic(n_fft)
+    w = hann_periodic(n_fft).to(spec.device)
     frames = torch.fft.irfft(spec.transpose(1, 2), n=n_fft, dim=-1) * w     # (B,T',n_fft)
     total = n_fft + hop * (n_frames - 1)
     fold = lambda cols: torch.nn.functional.fold(                    # noqa: E731
@@ -264,9 +264,9 @@ def fm_weighted_norm(spec: torch.Tensor, interp, n_fft: int, sr: int) -> torch.T
     B, F, Tn = spec.shape
     power = spec.abs() ** 2
     spl = 10.0 * torch.log10(power + 1e-10)
-    f = bin_frequencies(n_fft, sr).view(1, F, 1).expand(B, F, Tn)
-    q = torch.stack([spl, f], dim=-1).reshape(-1, 2).numpy()
-    w = torch.tensor(interp(q).reshape(B, F, Tn), dtype=torch.float32)
+    f = bin_frequencies(n_fft, sr).to(spec.device).view(1, F, 1).expand(B, F, Tn)
+    q = torch.stack([spl, f], dim=-1).reshape(-1, 2).detach().cpu().numpy()      # the D2H of projections.py:104
+    w = torch.tensor(interp(q).reshape(B, F, Tn), dtype=torch.float32, device=spec.device)
     return torch.sqrt((power * w).sum())
 
 
@@ -343,7 +343,7 @@ def constrain(p: torch.Tensor, clean: Optional[torch.Tensor], hp, interp=None,
         if kind in FREQ_NORMS:
             spec = stft(p, hp.n_fft, hp.hop_length)
             if kind == "min_max_freqs":
-                spec = spec * band_mask(hp.n_fft, hp.sr, hp.min_freq_attack, hp.max_freq_attack)
+                spec = spec * band_mask(hp.n_fft, hp.sr, hp.min_freq_attack, hp.max_freq_attack).to(spec.device)
             elif kind == "fletcher_munson":
                 spec = project_fm(spec, interp, hp.n_fft, hp.sr, hp.fm_epsilon)
             else:

@@ -98,9 +98,7 @@ int paa_destroy(paa_handle* h) {
     if (!h) return PAA_OK;
     cudaFree(h->d_blob);
     cudaFree(h->d_thr_tmp);
-    cudaFree(h->d_fm_cols);
-    cudaFree(h->d_fm_knots);
-    cudaFree(h->d_fm_inband);
+    cudaFree(h->d_fm_blob);
     delete h;
     return PAA_OK;
 }
@@ -127,36 +125,36 @@ int paa_scalars(const paa_handle* h, const void* scratch, float* out8, void* str
 int paa_set_fm_grid(paa_handle* h, const double* phon_knots, int n_phon, const double* freq_knots, int n_freq,
                     const double* values, double fill_value) {
     if (!h || !phon_knots || !freq_knots || !values) return PAA_ERR_NULL;
-    if (n_phon < 2 || n_freq < 2 || n_phon > 64) return PAA_ERR_SHAPE;
+    if (n_phon < 2 || n_freq < 2 || n_phon > 32) return PAA_ERR_SHAPE;      // table must fit shared memory next to the tile
     for (int i = 1; i < n_phon; ++i) if (!(phon_knots[i] > phon_knots[i - 1])) return PAA_ERR_SHAPE;
     for (int j = 1; j < n_freq; ++j) if (!(freq_knots[j] > freq_knots[j - 1])) return PAA_ERR_SHAPE;
-    std::vector<float> cols((size_t)h->F * n_phon), knots(n_phon);
-    std::vector<uint8_t> inband(h->F);
+    // blob = [64 floats: knots][n_phon rows of F floats]; rows are contiguous in k so a warp's lanes (consecutive
+    // bins) read neighbouring words, and the whole table rides the kernel's TMA bulk copy into shared memory
+    const size_t blob_floats = ((64 + (size_t)n_phon * h->F + 3) / 4) * 4;
+    std::vector<float> blob(blob_floats, 0.f);
     for (int k = 0; k < h->F; ++k) {
         const double f = (double)((float)k * h->bin_hz);         // the reference queries with fp32 bin centres
-        inband[k] = !(f < freq_knots[0] || f > freq_knots[n_freq - 1]);
+        const bool inband = !(f < freq_knots[0] || f > freq_knots[n_freq - 1]);
         int j = 0;
         while (j + 1 < n_freq - 1 && freq_knots[j + 1] < f) ++j;   // searchsorted(left) - 1, clipped
         const double t = (f - freq_knots[j]) / (freq_knots[j + 1] - freq_knots[j]);
         for (int i = 0; i < n_phon; ++i)
-            cols[(size_t)k * n_phon + i] =
-                inband[k] ? (float)((1.0 - t) * values[i * n_freq + j] + t * values[i * n_freq + j + 1]) : (float)fill_value;
+            blob[64 + (size_t)i * h->F + k] =
+                inband ? (float)((1.0 - t) * values[i * n_freq + j] + t * values[i * n_freq + j + 1]) : (float)fill_value;
     }
     bool uniform = true;
     const double dk = phon_knots[1] - phon_knots[0];
     for (int i = 0; i < n_phon; ++i) {
-        knots[i] = (float)phon_knots[i];
+        blob[i] = (float)phon_knots[i];
         if (i && std::fabs((phon_knots[i] - phon_knots[i - 1]) - dk) > 1e-12 * std::fabs(dk)) uniform = false;
     }
     PAA_CUDA(h, cudaSetDevice(h->device));
-    cudaFree(h->d_fm_cols); cudaFree(h->d_fm_knots); cudaFree(h->d_fm_inband);
-    h->d_fm_cols = nullptr; h->d_fm_knots = nullptr; h->d_fm_inband = nullptr;
-    PAA_CUDA(h, cudaMalloc((void**)&h->d_fm_cols, cols.size() * 4));
-    PAA_CUDA(h, cudaMalloc((void**)&h->d_fm_knots, knots.size() * 4));
-    PAA_CUDA(h, cudaMalloc((void**)&h->d_fm_inband, inband.size()));
-    PAA_CUDA(h, cudaMemcpy(h->d_fm_cols, cols.data(), cols.size() * 4, cudaMemcpyHostToDevice));
-    PAA_CUDA(h, cudaMemcpy(h->d_fm_knots, knots.data(), knots.size() * 4, cudaMemcpyHostToDevice));
-    PAA_CUDA(h, cudaMemcpy(h->d_fm_inband, inband.data(), inband.size(), cudaMemcpyHostToDevice));
+    cudaFree(h->d_fm_blob);
+    h->d_fm_blob = nullptr;
+    h->fm_blob_bytes = blob_floats * sizeof(float);
+    PAA_CUDA(h, cudaMalloc((void**)&h->d_fm_blob, h->fm_blob_bytes));
+    PAA_CUDA(h, cudaMemcpy(h->d_fm_blob, blob.data(), h->fm_blob_bytes, cudaMemcpyHostToDevice));
+    const float* knots = blob.data();
     h->fm_n_phon = n_phon;
     h->fm_fill = (float)fill_value;
     h->fm_uniform = uniform ? 1 : 0;

@@ -26,9 +26,8 @@ struct paa_handle {
     std::vector<float> h_window;
 
     // fletcher_munson penalty grid, frequency axis pre-interpolated per rfft bin
-    float* d_fm_cols = nullptr;      // [F][n_phon]  w(phon_knot i, f_k)
-    float* d_fm_knots = nullptr;     // [n_phon]
-    uint8_t* d_fm_inband = nullptr;  // [F] 1 when f_k inside the grid's frequency range
+    float* d_fm_blob = nullptr;      // [64: phon knots][n_phon x F: w(knot i, f_k)], fill outside the frequency axis
+    size_t fm_blob_bytes = 0;
     int fm_n_phon = 0;
     float fm_fill = 1.f;
     int fm_uniform = 0;              // knots equally spaced -> direct cell lookup

@@ -62,9 +62,8 @@ struct StftArgs {
     float2* spec_out;
     long long sb, sf, st;
     // fletcher_munson
-    const float* fm_cols;
-    const float* fm_knots;
-    const unsigned char* fm_inband;
+    const float* fm_blob;  // [64 floats: phon knots][fm_np x F floats: w(knot i, f_k), out-of-band bins = fill]
+    unsigned fm_blob_bytes;
     int fm_np, fm_uniform;
     float fm_fill, fm_k0, fm_inv_dk, fm_klast;
     double* partials;
@@ -76,8 +75,10 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -157,24 +158,25 @@ __device__ __forceinline__ void op_phon(const float* lim_c, int k, float c, floa
     im *= g;
 }
 // compute_fm_weighted_norm_interp (projections.py:93-113): P * w(10 log10(P+1e-10), f_k)
+// `tab` is the fm blob (global memory for the element-wise kernel, shared memory in the fused kernel).
 template <bool FAST>
-__device__ __forceinline__ float fm_term(const StftArgs& a, int k, float re, float im) {
+__device__ __forceinline__ float fm_term(const StftArgs& a, const float* __restrict__ tab, int F, int k, float re, float im) {
     const float m = sqrtf(fmaf(re, re, im * im));
     const float P = m * m;
     // FAST: MUFU.LG2 (abs error ~1e-6 dB, it only positions the query inside a 10 dB cell)
     const float spl = FAST ? 3.0102999566398120f * __log2f(P + 1e-10f) : 10.f * log10f(P + 1e-10f);
     float w = a.fm_fill;
-    if (a.fm_inband[k] && !(spl < a.fm_k0) && !(spl > a.fm_klast)) {
+    if (!(spl < a.fm_k0) && !(spl > a.fm_klast)) {       // bins outside the frequency axis hold `fill` in every row
         int i;
         if (a.fm_uniform) {
             i = (int)((spl - a.fm_k0) * a.fm_inv_dk);
         } else {
             i = 0;
-            for (int q = 1; q < a.fm_np - 1; ++q) i += (spl > a.fm_knots[q]) ? 1 : 0;
+            for (int q = 1; q < a.fm_np - 1; ++q) i += (spl > tab[q]) ? 1 : 0;
         }
         i = max(0, min(i, a.fm_np - 2));
-        const float k0 = a.fm_knots[i], k1 = a.fm_knots[i + 1];
-        const float c0 = __ldg(a.fm_cols + (size_t)k * a.fm_np + i), c1 = __ldg(a.fm_cols + (size_t)k * a.fm_np + i + 1);
+        const float k0 = tab[i], k1 = tab[i + 1];
+        const float c0 = tab[64 + i * F + k], c1 = tab[64 + (i + 1) * F + k];
         const float tp = FAST ? __fdividef(spl - k0, k1 - k0) : (spl - k0) / (k1 - k0);
         w = fmaf(tp, c1 - c0, c0);
     }
@@ -224,9 +226,9 @@ __device__ __forceinline__ void spectral_middle(const StftArgs& a, float2* buf, 
             Y = SELF ? X : a.spec_in[spec_off + (long long)kn * a.sf];
         }
         if (SINK == SINK_REDUCE) {
-            const float t0 = fm_term<true>(a, k, X.x, X.y);
+            const float t0 = fm_term<true>(a, tbl, N + 1, k, X.x, X.y);
             if (commit) acc += t0;
-            if (!SELF) acc += fm_term<true>(a, kn, Y.x, Y.y);
+            if (!SELF) acc += fm_term<true>(a, tbl, N + 1, kn, Y.x, Y.y);
             return;
         }
         apply_op<OP, TO_TIME>(a, tbl, scale, kC, k, X.x, X.y);
@@ -277,8 +279,9 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     const float4* s_tw = (const float4*)(sp + a.off_tw);
     const float2* s_post = (const float2*)(sp + a.off_post);
     sp += a.blob_bytes;
-    float* s_thr = (float*)sp;
+    float* s_thr = (float*)sp;                 // per-bin table of the operator: phon limits, or the fletcher_munson blob
     if (OP == OP_PHON || OP == OP_PHON_DB) sp += ((F * 4 + 15) / 16) * 16;
+    if (SINK == SINK_REDUCE) sp += a.fm_blob_bytes;
     float2* s_fft = (float2*)sp;
     sp += (size_t)kWarps * BufLayout<NFFT>::kFloat2 * sizeof(float2);
     float* s_in = (float*)sp;
@@ -292,7 +295,11 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
 
     if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
-    if (tid == 0) tma_bulk_g2s(s_win, a.blob, a.blob_bytes, &bar);
+    if (tid == 0) {
+        mbar_expect_tx(&bar, a.blob_bytes + (SINK == SINK_REDUCE ? a.fm_blob_bytes : 0u));
+        tma_bulk_g2s(s_win, a.blob, a.blob_bytes, &bar);
+        if (SINK == SINK_REDUCE) tma_bulk_g2s(s_thr, a.fm_blob, a.fm_blob_bytes, &bar);
+    }
 
     // ---- stage the input span (reflect padding at the row ends, PGD step fused) ----------------
     if (SRC == SRC_TIME) {
@@ -532,7 +539,7 @@ __global__ void k_spec_fm_partials(StftArgs a, int F) {
         if (a.sf <= a.st) { k = (int)(i % F); t = (int)((i / F) % a.n_frames); b = (int)(i / ((long long)F * a.n_frames)); }
         else { t = (int)(i % a.n_frames); k = (int)((i / a.n_frames) % F); b = (int)(i / ((long long)F * a.n_frames)); }
         const float2 X = a.spec_in[b * a.sb + k * a.sf + t * a.st];
-        acc += fm_term<false>(a, k, X.x, X.y);
+        acc += fm_term<false>(a, a.fm_blob, F, k, X.x, X.y);
     }
     __shared__ float sh[32];
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -552,6 +559,7 @@ size_t smem_bytes(const paa_handle* h, int src, int sink, int op, int FT, int S)
     constexpr int N = NFFT / 2;
     size_t b = h->blob_bytes;
     if (op == OP_PHON || op == OP_PHON_DB) b += (((N + 1) * 4 + 15) / 16) * 16;
+    if (sink == SINK_REDUCE) b += h->fm_blob_bytes;
     b += (size_t)kWarps * (N + N / 16) * sizeof(float2);
     if (src == SRC_TIME) b += (size_t)((FT - 1) * h->hop + NFFT) * 4;
     if (sink == SINK_TIME) b += (size_t)S * h->hop * 4;
@@ -586,7 +594,7 @@ void fill_common(const paa_handle* h, StftArgs& a, int rows, int T, int n_frames
     a.blob = h->d_blob; a.blob_bytes = (unsigned)h->blob_bytes;
     a.off_tw = (unsigned)h->off_twiddle; a.off_post = (unsigned)h->off_post;
     a.bin_hz = h->bin_hz;
-    a.fm_cols = h->d_fm_cols; a.fm_knots = h->d_fm_knots; a.fm_inband = h->d_fm_inband;
+    a.fm_blob = h->d_fm_blob; a.fm_blob_bytes = (unsigned)h->fm_blob_bytes;
     a.fm_np = h->fm_n_phon; a.fm_uniform = h->fm_uniform; a.fm_fill = h->fm_fill;
     a.fm_k0 = h->fm_k0; a.fm_klast = h->fm_klast; a.fm_inv_dk = h->fm_inv_dk;
 }
@@ -706,7 +714,7 @@ int paa_project_fletcher_munson(paa_handle* h, const float* p_in, float* p_out, 
                                 double fm_epsilon, int exact_roundtrip, const paa_step* step, void* scratch,
                                 void* stream) {
     if (!h || !p_in || !p_out || !scratch) return PAA_ERR_NULL;
-    if (!h->d_fm_cols) return PAA_ERR_STATE;
+    if (!h->d_fm_blob) return PAA_ERR_STATE;
     int rc = check_time_shape(h, rows, T);
     if (rc) return rc;
     if (out_len <= 0) return PAA_ERR_SHAPE;
@@ -811,7 +819,7 @@ int paa_spec_phon_level(paa_handle* h, const float* spec_in, float* spec_out, in
 static int spec_fm(paa_handle* h, const float* spec_in, float* spec_out, int rows, int n_frames, int64_t sb, int64_t sf,
                    int64_t stt, double fm_epsilon, int apply, void* scratch, cudaStream_t st) {
     if (!h || !spec_in || !scratch || (apply && !spec_out)) return PAA_ERR_NULL;
-    if (!h->d_fm_cols) return PAA_ERR_STATE;
+    if (!h->d_fm_blob) return PAA_ERR_STATE;
     if (rows <= 0 || n_frames <= 0) return PAA_ERR_SHAPE;
     StftArgs a{};
     fill_common(h, a, rows, 0, n_frames);

@@ -302,6 +302,21 @@ __global__ void __launch_bounds__(kThreads) k_scale(const float* q_in, float* p_
     }
 }
 
+// |x1-x0| + |x2-x1| + |x3-x2| + |next-x3| for the float4 whose first element sits in column `col` of a row of
+// length T >= 4; a pair is dropped when its left element is the last sample of a row (projections.py:58,62).
+__device__ __forceinline__ float tv_quad(float4 x, float nx, int col, int T, bool has_next) {
+    int c1 = col + 1, c2 = col + 2, c3 = col + 3;
+    if (c1 >= T) c1 -= T;
+    if (c2 >= T) c2 -= T;
+    if (c3 >= T) c3 -= T;
+    float t = 0.f;
+    if (col != T - 1) t += fabsf(x.y - x.x);
+    if (c1 != T - 1) t += fabsf(x.z - x.y);
+    if (c2 != T - 1) t += fabsf(x.w - x.z);
+    if (c3 != T - 1 && has_next) t += fabsf(nx - x.w);
+    return t;
+}
+
 // ---- kernel: the whole reducing projection in ONE cooperative launch ----------------------------
 // Phase A (step + reduce) -> grid barrier -> every block re-sums the partials in the same fixed
 // order -> phase B (rescale).  Each thread revisits exactly the float4s it produced in phase A, and
@@ -321,35 +336,47 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     float acc0 = 0.f, acc1 = 0.f;
     float4 keep[kRC];
 
-    auto phase_a = [&](int64_t i4) -> float4 {
+    // total variation: row-column of each thread's current float4, advanced without 64-bit division
+    const int lane = threadIdx.x & 31;
+    int colp = 0, stepp = 0;
+    if (NORM == NORM_TV) { colp = (int)((tid * 4) % a.T); stepp = (int)((nth * 4) % a.T); }
+
+    // phase A on one float4: step, accumulate the norm, hand back the stepped values.  For tv every lane of the
+    // warp calls it (act = in range): the element after the float4 comes from the next lane by shuffle, only the
+    // last lane (or the last float4) recomputes it from memory.
+    auto phase_a = [&](int64_t i4, bool act) -> float4 {
         const int64_t i = i4 * 4;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (NORM != NORM_TV) {
-            const float4 x = stepped4<STEP, true>(a.p_in, i, s);
-            acc0 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
-            return x;
+            if (act) {
+                x = stepped4<STEP, true>(a.p_in, i, s);
+                acc0 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+            }
         } else {
-            const float4 x = stepped4<STEP, false>(a.p_in, i, s);
-            const float nx = (i + 4 < a.n) ? stepped1<STEP, false>(a.p_in, i + 4, s) : 0.f;
-            const int c = (int)(i % a.T), Tp = a.T;
-            float t = 0.f;
-            if (c != Tp - 1) t += fabsf(x.y - x.x);
-            if ((c + 1) % Tp != Tp - 1) t += fabsf(x.z - x.y);
-            if ((c + 2) % Tp != Tp - 1) t += fabsf(x.w - x.z);
-            if ((c + 3) % Tp != Tp - 1 && i + 4 < a.n) t += fabsf(nx - x.w);
-            acc0 += t;
-            return x;
+            if (act) x = stepped4<STEP, false>(a.p_in, i, s);
+            float nx = __shfl_down_sync(0xffffffffu, x.x, 1);
+            const bool has_next = act && (i + 4 < a.n);
+            if (has_next && (lane == 31 || i4 + 1 >= n4)) nx = stepped1<STEP, false>(a.p_in, i + 4, s);
+            if (act) acc0 += tv_quad(x, nx, colp, a.T, has_next);
+            colp += stepp;
+            if (colp >= a.T) colp -= a.T;
         }
+        return x;
     };
 
 #pragma unroll
     for (int k = 0; k < kRC; ++k) {
         const int64_t i4 = tid + k * nth;
-        if (i4 < n4) keep[k] = phase_a(i4);
+        const bool act = i4 < n4;
+        if (NORM == NORM_TV || act) keep[k] = phase_a(i4, act);
     }
     {
         int k = kRC;
-        for (int64_t i4 = tid + kRC * nth; i4 < n4; i4 += nth, ++k) {
-            const float4 x = phase_a(i4);
+        // (i4 - lane) is warp-uniform: whole warps stay in the loop for the shuffles above
+        for (int64_t i4 = tid + kRC * nth; i4 - lane < n4; i4 += nth, ++k) {
+            const bool act = i4 < n4;
+            const float4 x = phase_a(i4, act);
+            if (!act) continue;
             if (k < kRC + sc_iters) cache[(k - kRC) * kFT + threadIdx.x] = x;
             else if (a.write_q) st4(a.q_out + i4 * 4, x);
         }
@@ -372,17 +399,19 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     } else if (NORM == NORM_TV) {
         const int64_t c4 = a.clean_n >> 2;
         const int Tc = a.clean_T;
-        for (int64_t i4 = tid; i4 < c4; i4 += nth) {
+        int colc = (int)((tid * 4) % Tc);
+        const int stepc = (int)((nth * 4) % Tc);
+        for (int64_t i4 = tid; i4 - lane < c4; i4 += nth) {
+            const bool act = i4 < c4;
             const int64_t i = i4 * 4;
-            const float4 x = ld4_stream(a.clean + i);
-            const float nx = (i + 4 < a.clean_n) ? a.clean[i + 4] : 0.f;
-            const int c = (int)(i % Tc);
-            float t = 0.f;
-            if (c != Tc - 1) t += fabsf(x.y - x.x);
-            if ((c + 1) % Tc != Tc - 1) t += fabsf(x.z - x.y);
-            if ((c + 2) % Tc != Tc - 1) t += fabsf(x.w - x.z);
-            if ((c + 3) % Tc != Tc - 1 && i + 4 < a.clean_n) t += fabsf(nx - x.w);
-            acc1 += t;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (act) x = ld4_stream(a.clean + i);
+            float nx = __shfl_down_sync(0xffffffffu, x.x, 1);
+            const bool has_next = act && (i + 4 < a.clean_n);
+            if (has_next && (lane == 31 || i4 + 1 >= c4)) nx = a.clean[i + 4];
+            if (act) acc1 += tv_quad(x, nx, colc, Tc, has_next);
+            colc += stepc;
+            if (colc >= Tc) colc -= Tc;
         }
         for (int64_t i = (c4 << 2) + tid; i < a.clean_n; i += nth)
             if ((int)(i % Tc) != Tc - 1 && i + 1 < a.clean_n) acc1 += fabsf(a.clean[i + 1] - a.clean[i]);
@@ -511,6 +540,7 @@ int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int
     a.partials = scratch_partials(scratch);
     a.write_q = (mode != PAA_STEP_NONE) || (src != p_out);
     bool vec = aligned16(src) && aligned16(p_out) && (NORM == NORM_L2 || aligned16(clean)) &&
+               (NORM != NORM_TV || (T >= 4 && clean_T >= 4)) &&
                (mode == PAA_STEP_NONE || aligned16(sd.grad)) &&
                (mode != PAA_STEP_ADAM || (aligned16(sd.m) && aligned16(sd.v)));
     int64_t work = std::max<int64_t>(n, a.clean_n);
