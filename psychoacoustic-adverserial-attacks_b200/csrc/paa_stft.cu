@@ -308,36 +308,56 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
         float* qr = (SINK == SINK_REDUCE && a.q_out) ? a.q_out + (size_t)row * a.T : nullptr;
         const int own_lo = NFFT / 2, own_hi = NFFT / 2 + FT * hop;   // SINK_REDUCE: samples this tile stores to q_out
         const int T = a.T;
-        for (int i4 = tid; i4 < lin / 4; i4 += kThreadsStft) {
-            const int i = i4 * 4, s = in0 + i;
-            float4 v;
-            if (a.vec_ok && s >= 0 && s + 3 < T) {
-                v = *reinterpret_cast<const float4*>(xr + s);
-                if (gr) {
-                    const float4 g = *reinterpret_cast<const float4*>(gr + s);
-                    v.x += a.lr * ((float)(g.x > 0.f) - (float)(g.x < 0.f));
-                    v.y += a.lr * ((float)(g.y > 0.f) - (float)(g.y < 0.f));
-                    v.z += a.lr * ((float)(g.z > 0.f) - (float)(g.z < 0.f));
-                    v.w += a.lr * ((float)(g.w > 0.f) - (float)(g.w < 0.f));
-                }
-                if (qr && i >= own_lo && i < own_hi) *reinterpret_cast<float4*>(qr + s) = v;
-            } else {
-                float e[4];
+        // All global loads of a chunk are issued before any of them is consumed (kStageUnroll x 2 float4 in flight
+        // per thread): the staging latency is otherwise exposed once per loop trip.
+        constexpr int kStageUnroll = 5;
+        const int lin4 = lin / 4;
+        for (int base4 = 0; base4 < lin4; base4 += kStageUnroll * kThreadsStft) {
+            float4 pv[kStageUnroll], gv[kStageUnroll];
+            bool fast[kStageUnroll];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    int sc = s + c;
-                    const bool inside = sc >= 0 && sc < T;
-                    if (sc < 0) sc = -sc;
-                    if (sc >= T) sc = 2 * (T - 1) - sc;
-                    sc = min(max(sc, 0), T - 1);
-                    float val = xr[sc];
-                    if (gr) { const float g = gr[sc]; val += a.lr * ((float)(g > 0.f) - (float)(g < 0.f)); }
-                    if (qr && inside && i + c >= own_lo && i + c < own_hi) qr[sc] = val;
-                    e[c] = val;
+            for (int u = 0; u < kStageUnroll; ++u) {
+                const int i4 = base4 + u * kThreadsStft + tid, s = in0 + i4 * 4;
+                fast[u] = i4 < lin4 && a.vec_ok && s >= 0 && s + 3 < T;
+                pv[u] = gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (fast[u]) {
+                    pv[u] = *reinterpret_cast<const float4*>(xr + s);
+                    if (gr) gv[u] = *reinterpret_cast<const float4*>(gr + s);
                 }
-                v = make_float4(e[0], e[1], e[2], e[3]);
             }
-            *reinterpret_cast<float4*>(s_in + i) = v;
+#pragma unroll
+            for (int u = 0; u < kStageUnroll; ++u) {
+                const int i4 = base4 + u * kThreadsStft + tid;
+                if (i4 >= lin4) continue;
+                const int i = i4 * 4, s = in0 + i;
+                float4 v = pv[u];
+                if (fast[u]) {
+                    if (gr) {
+                        const float4 g = gv[u];
+                        v.x += a.lr * ((float)(g.x > 0.f) - (float)(g.x < 0.f));
+                        v.y += a.lr * ((float)(g.y > 0.f) - (float)(g.y < 0.f));
+                        v.z += a.lr * ((float)(g.z > 0.f) - (float)(g.z < 0.f));
+                        v.w += a.lr * ((float)(g.w > 0.f) - (float)(g.w < 0.f));
+                    }
+                    if (qr && i >= own_lo && i < own_hi) *reinterpret_cast<float4*>(qr + s) = v;
+                } else {
+                    float e[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        int sc = s + c;
+                        const bool inside = sc >= 0 && sc < T;
+                        if (sc < 0) sc = -sc;
+                        if (sc >= T) sc = 2 * (T - 1) - sc;
+                        sc = min(max(sc, 0), T - 1);
+                        float val = xr[sc];
+                        if (gr) { const float g = gr[sc]; val += a.lr * ((float)(g > 0.f) - (float)(g < 0.f)); }
+                        if (qr && inside && i + c >= own_lo && i + c < own_hi) qr[sc] = val;
+                        e[c] = val;
+                    }
+                    v = make_float4(e[0], e[1], e[2], e[3]);
+                }
+                *reinterpret_cast<float4*>(s_in + i) = v;
+            }
         }
     }
     if (SINK == SINK_TIME)
@@ -368,7 +388,14 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     // ---- frames ----------------------------------------------------------------------------------
     float2* buf = s_fft + (size_t)warp * BufLayout<NFFT>::kFloat2;
     const LaneBase<NFFT> lb(lane);
-    const float2* win2 = reinterpret_cast<const float2*>(s_win);
+    // this lane's slice of the (halved) window lives in registers for the whole tile: the first forward stage and the
+    // last inverse stage touch the same points m = lane + 32*j, j = 0 .. N/32-1 (saves 64 smem wavefronts per frame)
+    float2 wreg[N / 32];
+    if (SRC == SRC_TIME || SINK == SINK_TIME) {
+        const float2* win2 = reinterpret_cast<const float2*>(s_win);
+#pragma unroll
+        for (int j = 0; j < N / 32; ++j) wreg[j] = win2[lane + 32 * j];
+    }
     float acc = 0.f;
     for (int r = 0; r < R; ++r) {
         for (int q = 0; q < a.Q; ++q) {
@@ -380,7 +407,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
                 const float2* x2 = reinterpret_cast<const float2*>(s_in + f * hop);
                 fft_warp<NFFT, -1>(
                     buf, s_tw, lane, lb,
-                    [&](int m, int) { const float2 xv = x2[m], wv = win2[m]; return make_float2(xv.x * wv.x, xv.y * wv.y); },
+                    [&](int m, int c) { const float2 xv = x2[m], wv = wreg[c / 32]; return make_float2(xv.x * wv.x, xv.y * wv.y); },
                     [&](int, int c, float2 v) { buf[lb.ld + padc(c)] = v; });
                 __syncwarp();
             }
@@ -391,10 +418,10 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
                 const int olim = S * hop;
                 fft_warp<NFFT, +1>(
                     buf, s_tw, lane, lb, [&](int, int c) { return buf[lb.ld + padc(c)]; },
-                    [&](int m, int, float2 v) {
+                    [&](int m, int c, float2 v) {
                         const int o = obase + 2 * m;
                         if (o >= 0 && o < olim) {
-                            const float2 wv = win2[m];
+                            const float2 wv = wreg[c / 32];
                             float2* dst = reinterpret_cast<float2*>(s_ola + o);
                             float2 cur = *dst;
                             cur.x += v.x * wv.x;

@@ -65,6 +65,30 @@ __device__ __forceinline__ float stepped1(const float* p, int64_t i, const StepD
     return x;
 }
 
+// The same in two halves, so that the loads of the next float4 can be issued before the arithmetic on the
+// current one (software pipelining in k_fused: memory-level parallelism, not instruction count, bounds it).
+struct Raw4 { float4 p, g, m, v; };
+template <int STEP>
+__device__ __forceinline__ Raw4 load_raw4(const float* p, int64_t i, const StepDev& s) {
+    Raw4 r;
+    r.p = ld4(p + i);
+    r.g = r.m = r.v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (STEP != PAA_STEP_NONE) r.g = ld4(s.grad + i);
+    if (STEP == PAA_STEP_ADAM) { r.m = ld4(s.m + i); r.v = ld4(s.v + i); }
+    return r;
+}
+template <int STEP, bool WRITE_STATE>
+__device__ __forceinline__ float4 finish4(Raw4 r, int64_t i, const StepDev& s) {
+    if (STEP == PAA_STEP_NONE) return r.p;
+    float4 x = r.p;
+    x.x = step_one<STEP>(x.x, r.g.x, r.m.x, r.v.x, s);
+    x.y = step_one<STEP>(x.y, r.g.y, r.m.y, r.v.y, s);
+    x.z = step_one<STEP>(x.z, r.g.z, r.m.z, r.v.z, s);
+    x.w = step_one<STEP>(x.w, r.g.w, r.m.w, r.v.w, s);
+    if (STEP == PAA_STEP_ADAM && WRITE_STATE) { st4(s.m + i, r.m); st4(s.v + i, r.v); }
+    return x;
+}
+
 // torch.clamp: NaN stays NaN, bounds applied as min(max(x, lo), hi)
 __device__ __forceinline__ float clamp1(float x, float lo, float hi) {
     return (x != x) ? x : fminf(fmaxf(x, lo), hi);
@@ -334,26 +358,27 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     const int64_t tid = (int64_t)blockIdx.x * kFT + threadIdx.x, nth = (int64_t)gridDim.x * kFT;
     const int64_t n4 = a.n >> 2;
     float acc0 = 0.f, acc1 = 0.f;
-    float4 keep[kRC];
+    constexpr int RCN = (STEP == PAA_STEP_ADAM) ? 2 : kRC;      // Adam carries 4 streams: fewer register-resident float4s
+    float4 keep[RCN];
 
     // total variation: row-column of each thread's current float4, advanced without 64-bit division
     const int lane = threadIdx.x & 31;
     int colp = 0, stepp = 0;
     if (NORM == NORM_TV) { colp = (int)((tid * 4) % a.T); stepp = (int)((nth * 4) % a.T); }
 
-    // phase A on one float4: step, accumulate the norm, hand back the stepped values.  For tv every lane of the
-    // warp calls it (act = in range): the element after the float4 comes from the next lane by shuffle, only the
-    // last lane (or the last float4) recomputes it from memory.
-    auto phase_a = [&](int64_t i4, bool act) -> float4 {
+    // phase A on one float4 whose operands are already in registers: step, accumulate the norm, hand back the
+    // stepped values.  For tv every lane of the warp calls it (act = in range): the element after the float4 comes
+    // from the next lane by shuffle, only the last lane (or the last float4) recomputes it from memory.
+    auto phase_a = [&](const Raw4& raw, int64_t i4, bool act) -> float4 {
         const int64_t i = i4 * 4;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (NORM != NORM_TV) {
             if (act) {
-                x = stepped4<STEP, true>(a.p_in, i, s);
+                x = finish4<STEP, true>(raw, i, s);
                 acc0 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
             }
         } else {
-            if (act) x = stepped4<STEP, false>(a.p_in, i, s);
+            if (act) x = finish4<STEP, false>(raw, i, s);
             float nx = __shfl_down_sync(0xffffffffu, x.x, 1);
             const bool has_next = act && (i + 4 < a.n);
             if (has_next && (lane == 31 || i4 + 1 >= n4)) nx = stepped1<STEP, false>(a.p_in, i + 4, s);
@@ -363,22 +388,40 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
         }
         return x;
     };
+    auto fetch = [&](int64_t i4, bool act) -> Raw4 {
+        Raw4 r;
+        r.p = r.g = r.m = r.v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) r = load_raw4<STEP>(a.p_in, i4 * 4, s);
+        return r;
+    };
 
+    {   // the first RCN float4s: all loads in flight at once, results stay in registers
+        Raw4 raw[RCN];
 #pragma unroll
-    for (int k = 0; k < kRC; ++k) {
-        const int64_t i4 = tid + k * nth;
-        const bool act = i4 < n4;
-        if (NORM == NORM_TV || act) keep[k] = phase_a(i4, act);
-    }
-    {
-        int k = kRC;
-        // (i4 - lane) is warp-uniform: whole warps stay in the loop for the shuffles above
-        for (int64_t i4 = tid + kRC * nth; i4 - lane < n4; i4 += nth, ++k) {
+        for (int k = 0; k < RCN; ++k) raw[k] = fetch(tid + k * nth, tid + k * nth < n4);
+#pragma unroll
+        for (int k = 0; k < RCN; ++k) {
+            const int64_t i4 = tid + k * nth;
             const bool act = i4 < n4;
-            const float4 x = phase_a(i4, act);
-            if (!act) continue;
-            if (k < kRC + sc_iters) cache[(k - kRC) * kFT + threadIdx.x] = x;
-            else if (a.write_q) st4(a.q_out + i4 * 4, x);
+            if (NORM == NORM_TV || act) keep[k] = phase_a(raw[k], i4, act);
+        }
+    }
+    {   // the rest, software-pipelined two deep; (i4 - lane) is warp-uniform so whole warps stay for the shuffles
+        int k = RCN;
+        int64_t i4 = tid + RCN * nth;
+        Raw4 cur = fetch(i4, i4 < n4);
+        while (i4 - lane < n4) {
+            const int64_t i4n = i4 + nth;
+            const Raw4 nxt = fetch(i4n, i4n < n4);
+            const bool act = i4 < n4;
+            const float4 x = phase_a(cur, i4, act);
+            if (act) {
+                if (k < RCN + sc_iters) cache[(k - RCN) * kFT + threadIdx.x] = x;
+                else if (a.write_q) st4(a.q_out + i4 * 4, x);
+            }
+            cur = nxt;
+            i4 = i4n;
+            ++k;
         }
     }
     if (tid == 0) {                                         // the n % 4 trailing elements go through global memory
@@ -391,6 +434,7 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     }
     if (NORM == NORM_SNR) {
         const int64_t c4 = a.clean_n >> 2;
+#pragma unroll 4
         for (int64_t i = tid; i < c4; i += nth) {
             const float4 c = ld4_stream(a.clean + i * 4);
             acc1 += (c.x * c.x + c.y * c.y) + (c.z * c.z + c.w * c.w);
@@ -401,6 +445,7 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
         const int Tc = a.clean_T;
         int colc = (int)((tid * 4) % Tc);
         const int stepc = (int)((nth * 4) % Tc);
+#pragma unroll 4
         for (int64_t i4 = tid; i4 - lane < c4; i4 += nth) {
             const bool act = i4 < c4;
             const int64_t i = i4 * 4;
@@ -448,14 +493,14 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
 
     auto scaled = [sc](float4 x) { x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; return x; };
 #pragma unroll
-    for (int k = 0; k < kRC; ++k) {
+    for (int k = 0; k < RCN; ++k) {
         const int64_t i4 = tid + k * nth;
         if (i4 < n4) st4(a.q_out + i4 * 4, scaled(keep[k]));
     }
     {
-        int k = kRC;
-        for (int64_t i4 = tid + kRC * nth; i4 < n4; i4 += nth, ++k) {
-            if (k < kRC + sc_iters) st4(a.q_out + i4 * 4, scaled(cache[(k - kRC) * kFT + threadIdx.x]));
+        int k = RCN;
+        for (int64_t i4 = tid + RCN * nth; i4 < n4; i4 += nth, ++k) {
+            if (k < RCN + sc_iters) st4(a.q_out + i4 * 4, scaled(cache[(k - RCN) * kFT + threadIdx.x]));
             else if (sc != 1.f) st4(a.q_out + i4 * 4, scaled(ld4(a.q_out + i4 * 4)));
         }
     }
@@ -559,7 +604,7 @@ int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int
         const int64_t work4 = (work + 3) / 4;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, (work4 + kFT - 1) / kFT));
         const int64_t iters = ((n >> 2) + (int64_t)grid * kFT - 1) / ((int64_t)grid * kFT);
-        int sc_iters = (int)std::max<int64_t>(0, std::min<int64_t>(kSCMax, iters - kRC));
+        int sc_iters = (int)std::max<int64_t>(0, std::min<int64_t>(kSCMax, iters - (mode == PAA_STEP_ADAM ? 2 : kRC)));
         size_t smem = (size_t)sc_iters * kFT * sizeof(float4);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSCMax * kFT * sizeof(float4)));
         f.nblocks = grid;
