@@ -524,10 +524,31 @@ __global__ void k_fm_finalize(const double* partials, int nblocks, float* scalar
 __global__ void k_fm_scale_identity(const float* __restrict__ q, float* __restrict__ out, int rows, int T, int out_len,
                                     int valid, const float* __restrict__ scalars) {
     const float sc = scalars[PAA_S_SCALE];
-    const long long n = (long long)rows * out_len;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(i / out_len), c = (int)(i - (long long)r * out_len);
-        out[i] = (c < valid && c < T) ? q[(size_t)r * T + c] * sc : 0.f;
+    const int lim = min(valid, T);
+    const bool vec = (T % 4 == 0) && (out_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+    const int cols4 = (out_len + 3) / 4;                       // float4 columns per row
+    const long long n4 = (long long)rows * cols4;
+    // (row, column) advance incrementally: no 64-bit division per element
+    long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    int r = (int)(i4 / cols4), c4 = (int)(i4 - (long long)r * cols4);
+    const int dr = (int)(stride / cols4), dc = (int)(stride - (long long)dr * cols4);
+    for (; i4 < n4; i4 += stride) {
+        const int c = c4 * 4;
+        const float* src = q + (size_t)r * T + c;
+        float* dst = out + (size_t)r * out_len + c;
+        if (vec && c + 3 < lim) {
+            float4 v = *reinterpret_cast<const float4*>(src);
+            v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+            *reinterpret_cast<float4*>(dst) = v;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (c + e < out_len) dst[e] = (c + e < lim) ? src[e] * sc : 0.f;
+        }
+        r += dr; c4 += dc;
+        if (c4 >= cols4) { c4 -= cols4; ++r; }
     }
 }
 
@@ -774,7 +795,7 @@ int paa_project_fletcher_munson(paa_handle* h, const float* p_in, float* p_out, 
         b.scalars = scalars;
         return run_fused<OP_SCALE>(h, b, q, nullptr, 0.f, p_out, rows, T, out_len, st);
     }
-    const long long n = (long long)rows * out_len;
+    const long long n = (long long)rows * ((out_len + 3) / 4);
     const int g2 = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8);
     k_fm_scale_identity<<<std::max(g2, 1), 256, 0, st>>>(q, p_out, rows, T, out_len, h->hop * (n_frames - 1), scalars);
     PAA_LAUNCH_CHECK(h);
