@@ -324,7 +324,46 @@ def projection_sweep(dev, iters: int = 20):
             out[name]["torch_eager_ms"] = f"unavailable: {type(exc).__name__}"
         del clean, p, grad
         torch.cuda.empty_cache()
+    out.update(compose_sweep(dev, flush, peak, iters))
     return out
+
+
+def compose_sweep(dev, flush, peak, iters):
+    """The input side: x_adv = clamp(clean + p) and dL/dp, universal (1,T) and per-utterance p,
+    batch 32 x 10 s; torch eager (add, clamp_, autograd's mask + batch sum) timed beside it."""
+    from paa_b200.core.compose import compose_clamp
+    B, T = BATCH, SECONDS * SR
+    g = torch.Generator(device=dev).manual_seed(7)
+    clean = (torch.rand(B, T, generator=g, device=dev) * 2 - 1) * 0.9
+    w = torch.randn(B, T, generator=g, device=dev)
+    res = {}
+    for rows in (1, B):
+        p = (torch.randn(rows, T, generator=g, device=dev) * 0.3).requires_grad_(True)
+
+        def timed(fn):
+            ts = []
+            for _ in range(iters):
+                flush.zero_()
+                torch.cuda._sleep(400_000)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return statistics.median(ts), r
+
+        fwd_ms, x = timed(lambda: compose_clamp(clean, p))
+        bwd_ms, _ = timed(lambda: torch.autograd.grad(x, p, w, retain_graph=True))
+        tf_ms, xt = timed(lambda: (clean + p).clamp_(-1.0, 1.0))
+        tb_ms, _ = timed(lambda: torch.autograd.grad(xt, p, w, retain_graph=True))
+        fb, bb = 8 * B * T + 4 * rows * T, 8 * B * T + 8 * rows * T       # algorithmic bytes: fwd R clean,p W x; bwd R clean,g,p W gp
+        tag = "universal" if rows == 1 else "per_utterance"
+        res[f"compose_fwd_{tag}"] = {"shape": f"{B}x{SECONDS}s", "ms": round(fwd_ms, 4), "GB/s": round(fb / fwd_ms / 1e6, 1),
+                                     "frac_of_measured_peak": round(fb / fwd_ms / 1e6 / peak, 4), "torch_eager_ms": round(tf_ms, 4)}
+        res[f"compose_bwd_{tag}"] = {"shape": f"{B}x{SECONDS}s", "ms": round(bwd_ms, 4), "GB/s": round(bb / bwd_ms / 1e6, 1),
+                                     "frac_of_measured_peak": round(bb / bwd_ms / 1e6 / peak, 4), "torch_eager_ms": round(tb_ms, 4)}
+    return res
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -148,7 +148,10 @@ int paa_spec_fm_project(paa_handle* h, const float* spec_in, float* spec_out, in
 /* ---- the input side of the path: x_adv = clamp(clean + p, -1, 1), train.py:136 - */
 int paa_compose_clamp(paa_handle* h, const float* clean, int clean_rows, const float* p, int p_rows, int T,
                       float* x_adv, void* stream);
-/* dL/dp from dL/dx_adv: masked by |clean+p| < 1 ... kept on autograd for now (not exported). */
+/* its backward: grad_p[b or 0, t] = (sum over b of) grad_x_adv[b,t] * 1[-1 <= clean[b,t]+p[.,t] <= 1]  (torch's clamp mask);
+ * for a universal (1,T) p the batch is summed in row order. */
+int paa_compose_clamp_backward(paa_handle* h, const float* clean, int clean_rows, const float* p, int p_rows, int T,
+                               const float* grad_x_adv, float* grad_p, void* stream);
 
 /* ---- WER counters (loss_helpers.py:25-32; evaluate/jiwer semantics): sum(S+D+I), sum(ref words) */
 int paa_wer_counts(const char* const* references, const char* const* hypotheses, int n,

@@ -1,1 +1,1 @@
-from . import fourier_transforms, iso, loss_helpers, projections  # noqa: F401
+from . import compose, fourier_transforms, iso, loss_helpers, projections  # noqa: F401

@@ -508,24 +508,71 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
         for (int64_t i = n4 << 2; i < a.n; ++i) a.q_out[i] *= sc;
 }
 
-// ---- kernel: compose + clamp (train.py:136): x_adv[b,t] = clamp(clean[b,t] + p[b % p_rows, t]) --
+// ---- kernels: compose + clamp (train.py:136) and its backward -- the input side of the path ----
+//   forward : x_adv[b,t] = clamp(clean[b,t] + p[b or 0, t], -1, 1)
+//   backward: dL/dp[b or 0, t] = (sum over b of) dL/dx_adv[b,t] * 1[-1 <= clean[b,t] + p[.,t] <= 1]   (torch's clamp mask)
+// grid.x covers float4 columns, grid.y strides over rows; a universal (1,T) p is re-read from L2, never from HBM.
 template <bool VEC>
 __global__ void __launch_bounds__(kThreads) k_compose(const float* __restrict__ clean, const float* __restrict__ p,
                                                      float* __restrict__ out, int rows, int p_rows, int T) {
-    const int64_t n = (int64_t)rows * T;
-    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x, nth = (int64_t)gridDim.x * kThreads;
-    if (VEC) {
-        const int64_t n4 = n >> 2;
-        for (int64_t i4 = tid; i4 < n4; i4 += nth) {
-            const int64_t i = i4 * 4;
-            const int64_t pi = p_rows == 1 ? i % T : i;
-            float4 c = ld4_stream(clean + i), q = ld4(p + pi);
-            c.x = clamp1(c.x + q.x, -1.f, 1.f); c.y = clamp1(c.y + q.y, -1.f, 1.f);
-            c.z = clamp1(c.z + q.z, -1.f, 1.f); c.w = clamp1(c.w + q.w, -1.f, 1.f);
-            st4(out + i, c);
+    const int W = VEC ? 4 : 1;
+    const int cols = (T + W - 1) / W;
+    for (int c = blockIdx.x * kThreads + threadIdx.x; c < cols; c += gridDim.x * kThreads) {
+        for (int b = blockIdx.y; b < rows; b += gridDim.y) {
+            const size_t i = (size_t)b * T + (size_t)c * W, pi = (p_rows == 1 ? 0 : (size_t)b * T) + (size_t)c * W;
+            if (VEC) {
+                float4 x = ld4_stream(clean + i);
+                const float4 q = ld4(p + pi);
+                x.x = clamp1(x.x + q.x, -1.f, 1.f); x.y = clamp1(x.y + q.y, -1.f, 1.f);
+                x.z = clamp1(x.z + q.z, -1.f, 1.f); x.w = clamp1(x.w + q.w, -1.f, 1.f);
+                st4(out + i, x);
+            } else {
+                out[i] = clamp1(clean[i] + p[pi], -1.f, 1.f);
+            }
         }
-    } else {
-        for (int64_t i = tid; i < n; i += nth) out[i] = clamp1(clean[i] + p[p_rows == 1 ? i % T : i], -1.f, 1.f);
+    }
+}
+
+__device__ __forceinline__ float pass1(float x, float q, float g) {
+    const float s = x + q;
+    return (s >= -1.f && s <= 1.f) ? g : 0.f;                  // NaN input: mask false, as torch's comparison
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) k_compose_bwd(const float* __restrict__ clean, const float* __restrict__ p,
+                                                         const float* __restrict__ gx, float* __restrict__ gp,
+                                                         int rows, int p_rows, int T) {
+    const int W = VEC ? 4 : 1;
+    const int cols = (T + W - 1) / W;
+    for (int c = blockIdx.x * kThreads + threadIdx.x; c < cols; c += gridDim.x * kThreads) {
+        if (p_rows == 1) {
+            // universal perturbation: sum over the batch in row order (fixed, deterministic)
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (VEC) q = ld4(p + (size_t)c * 4); else q.x = p[c];
+#pragma unroll 4
+            for (int b = 0; b < rows; ++b) {
+                const size_t i = (size_t)b * T + (size_t)c * W;
+                if (VEC) {
+                    const float4 x = ld4_stream(clean + i), g = ld4_stream(gx + i);
+                    acc.x += pass1(x.x, q.x, g.x); acc.y += pass1(x.y, q.y, g.y);
+                    acc.z += pass1(x.z, q.z, g.z); acc.w += pass1(x.w, q.w, g.w);
+                } else {
+                    acc.x += pass1(clean[i], q.x, gx[i]);
+                }
+            }
+            if (VEC) st4(gp + (size_t)c * 4, acc); else gp[c] = acc.x;
+        } else {
+            for (int b = blockIdx.y; b < rows; b += gridDim.y) {
+                const size_t i = (size_t)b * T + (size_t)c * W;
+                if (VEC) {
+                    const float4 x = ld4_stream(clean + i), q = ld4(p + i), g = ld4_stream(gx + i);
+                    st4(gp + i, make_float4(pass1(x.x, q.x, g.x), pass1(x.y, q.y, g.y), pass1(x.z, q.z, g.z), pass1(x.w, q.w, g.w)));
+                } else {
+                    gp[i] = pass1(clean[i], p[i], gx[i]);
+                }
+            }
+        }
     }
 }
 
@@ -721,15 +768,33 @@ int paa_project_tv(paa_handle* h, const float* p_in, float* p_out, int rows, int
                                    (float)tv_epsilon, 0.0, step, scratch, (cudaStream_t)stream);
 }
 
+static dim3 compose_grid(const paa_handle* h, int cols, int rows, bool row_parallel) {
+    const int gx = std::max(1, std::min((cols + kThreads - 1) / kThreads, h->num_sms * kBlocksPerSm));
+    int gy = 1;
+    if (row_parallel) gy = std::max(1, std::min(rows, (h->num_sms * kBlocksPerSm + gx - 1) / gx));
+    return dim3(gx, gy, 1);
+}
+
 int paa_compose_clamp(paa_handle* h, const float* clean, int clean_rows, const float* p, int p_rows, int T,
                       float* x_adv, void* stream) {
     if (!h || !clean || !p || !x_adv) return PAA_ERR_NULL;
     if (clean_rows <= 0 || T <= 0 || (p_rows != 1 && p_rows != clean_rows)) return PAA_ERR_SHAPE;
-    const int64_t n = (int64_t)clean_rows * T;
-    bool vec = aligned16(clean) && aligned16(p) && aligned16(x_adv) && (T % 4 == 0);
-    int grid = grid_for(h, vec ? (n + 3) / 4 : n);
+    const bool vec = aligned16(clean) && aligned16(p) && aligned16(x_adv) && (T % 4 == 0);
+    const dim3 grid = compose_grid(h, vec ? T / 4 : T, clean_rows, true);
     if (vec) k_compose<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(clean, p, x_adv, clean_rows, p_rows, T);
     else k_compose<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(clean, p, x_adv, clean_rows, p_rows, T);
+    PAA_LAUNCH_CHECK(h);
+    return PAA_OK;
+}
+
+int paa_compose_clamp_backward(paa_handle* h, const float* clean, int clean_rows, const float* p, int p_rows, int T,
+                               const float* grad_x_adv, float* grad_p, void* stream) {
+    if (!h || !clean || !p || !grad_x_adv || !grad_p) return PAA_ERR_NULL;
+    if (clean_rows <= 0 || T <= 0 || (p_rows != 1 && p_rows != clean_rows)) return PAA_ERR_SHAPE;
+    const bool vec = aligned16(clean) && aligned16(p) && aligned16(grad_x_adv) && aligned16(grad_p) && (T % 4 == 0);
+    const dim3 grid = compose_grid(h, vec ? T / 4 : T, clean_rows, p_rows != 1);
+    if (vec) k_compose_bwd<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(clean, p, grad_x_adv, grad_p, clean_rows, p_rows, T);
+    else k_compose_bwd<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(clean, p, grad_x_adv, grad_p, clean_rows, p_rows, T);
     PAA_LAUNCH_CHECK(h);
     return PAA_OK;
 }

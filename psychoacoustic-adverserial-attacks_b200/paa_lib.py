@@ -28,6 +28,7 @@ EXPORTS = (
     "paa_project_linf paa_project_l2 paa_project_snr paa_project_tv paa_project_min_max_freqs "
     "paa_project_max_phon paa_project_fletcher_munson paa_step_only paa_stft paa_istft "
     "paa_spec_min_max_freqs paa_spec_phon_level paa_spec_fm_norm paa_spec_fm_project paa_compose_clamp "
+    "paa_compose_clamp_backward "
     "paa_wer_counts"
 ).split()
 
@@ -79,6 +80,7 @@ def _load() -> C.CDLL:
         "paa_spec_fm_norm": (i32, [vp, vp, i32, i32, i64, i64, i64, vp, vp]),
         "paa_spec_fm_project": (i32, [vp, vp, vp, i32, i32, i64, i64, i64, f64, vp, vp]),
         "paa_compose_clamp": (i32, [vp, vp, i32, vp, i32, i32, vp, vp]),
+        "paa_compose_clamp_backward": (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp]),
         "paa_wer_counts": (i32, [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), i32, C.POINTER(i64), C.POINTER(i64)]),
     }
     for name in EXPORTS:

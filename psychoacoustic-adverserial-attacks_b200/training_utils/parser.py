@@ -32,4 +32,6 @@ def create_arg_parser():
     p.add_argument("--device", type=str, default="cuda")
     # not in the reference: waive the bit-faithful STFT->scale->ISTFT second pass of fletcher_munson
     p.add_argument("--fm_identity_roundtrip", action="store_true")
+    # not in the reference: x_adv = clamp(clean + p) and its backward as libpaa kernels instead of autograd's passes
+    p.add_argument("--fused_compose", action="store_true")
     return p

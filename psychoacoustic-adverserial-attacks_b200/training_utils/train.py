@@ -12,10 +12,10 @@ import torch
 
 try:
     from .. import paa_lib as L
-    from ..core import projections
+    from ..core import compose, projections
 except ImportError:
     import paa_lib as L
-    from core import projections
+    from core import compose, projections
 
 logger = logging.getLogger("asr_attack")
 
@@ -141,7 +141,10 @@ def train_epoch(args, train_data_loader, p, model, epoch, processor, interp, wer
         p.requires_grad_(True)
         if p.grad is not None:
             p.grad = None
-        perturbed = (clean_audio + p).clamp_(-1.0, 1.0)
+        if getattr(args, "fused_compose", False):          # one kernel forward, one backward (core/compose.py)
+            perturbed = compose.compose_clamp(clean_audio, p)
+        else:
+            perturbed = (clean_audio + p).clamp_(-1.0, 1.0)
         loss, logits = loss_helpers.get_loss_for_training(model=model, data=perturbed, target_texts=target_texts,
                                                           processor=processor, args=args)
         ctc_scores.append(float(loss.item()))

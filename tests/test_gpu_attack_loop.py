@@ -26,6 +26,7 @@ def test_train_epoch_runs_and_constrains(norm, opt):
         ["--norm_type", norm, "--optimizer_type", opt, "--snr_db", "30", "--lr", "1e-3", "--l2_size", "0.5",
          "--linf_size", "0.002", "--fm_epsilon", "5", "--attack_mode", "targeted" if norm == "snr" else "untargeted"])
     args.device = str(dev)
+    args.fused_compose = (opt == "adam")               # exercise both composes: autograd's and libpaa's kernels
     model = tiny_model(dev)
     for q in model.parameters():
         q.requires_grad_(False)

@@ -258,3 +258,26 @@ def test_full_size_properties(norm, B, T, sigma, env):
             from paa_b200 import paa_lib as L
             s = L.plan_for(p, args).scalars()
             assert 0.0 < s[L.S_SCALE] <= 1.0 and s[L.S_NORM] > 0.0
+
+
+@pytest.mark.parametrize("rows,B,T", [(1, 5, 16000), (5, 5, 16000), (1, 3, 4999), (3, 3, 4999)])
+def test_compose_clamp_forward_backward(rows, B, T, env):
+    """x_adv = clamp(clean + p, -1, 1) and dL/dp against torch autograd (train.py:136), incl. saturated samples."""
+    from paa_b200.core.compose import compose_clamp
+    g = torch.Generator().manual_seed(T + rows)
+    clean = ((torch.rand(B, T, generator=g) * 2 - 1) * 0.9).cuda()
+    p0 = (torch.randn(rows, T, generator=g) * 0.3).cuda()
+    clean[0, :7] = torch.tensor([1.0, -1.0, 0.5, 2.0, -2.0, 0.999, float("nan")])
+    p0[0, :7] = torch.tensor([0.0, 0.0, 0.5, 0.0, 0.0, 0.001, 0.0])          # sums of exactly +-1 pass gradient
+    w = torch.randn(B, T, generator=g).cuda()
+    pa = p0.clone().requires_grad_(True)
+    ref = (clean + pa).clamp_(-1.0, 1.0)
+    (ref * w).nan_to_num().sum().backward()
+    pb = p0.clone().requires_grad_(True)
+    out = compose_clamp(clean, pb)
+    (out * w).nan_to_num().sum().backward()
+    assert torch.equal(out.nan_to_num(7.0), ref.detach().nan_to_num(7.0))
+    if rows == B:
+        assert torch.equal(pb.grad, pa.grad)                                    # element-wise: bit exact
+    else:
+        assert rel_max(pb.grad, pa.grad) < 1e-6                                 # batch sum: order of additions only
