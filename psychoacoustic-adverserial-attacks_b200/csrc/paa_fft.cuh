@@ -17,11 +17,23 @@
 namespace paa {
 
 template <int NFFT> struct Plan;
-template <> struct Plan<1024> { static constexpr int N = 512, R0 = 8, R1 = 8, R2 = 8; };
-template <> struct Plan<512>  { static constexpr int N = 256, R0 = 4, R1 = 8, R2 = 8; };
+// padB: the layout of the second exchange (stage-1 stores / stage-2 loads).  Each exchange is a complete
+// write-then-read of the buffer, so it may use its own padding: padc (= i + i/16) makes the stride-R0 stores of
+// stage 0 conflict free, padB makes the (j/R0)*R0*R1 + j%R0 + r*R0 stores of stage 1 conflict free, and both keep
+// the contiguous loads conflict free and every address = per-lane base + compile-time offset.
+template <> struct Plan<1024> {
+    static constexpr int N = 512, R0 = 8, R1 = 8, R2 = 8;
+    __host__ __device__ static constexpr int padB(int i) { return i + (i >> 4) + 4 * (i >> 6); }
+};
+template <> struct Plan<512> {
+    static constexpr int N = 256, R0 = 4, R1 = 8, R2 = 8;
+    __host__ __device__ static constexpr int padB(int i) { return i + 4 * (i >> 5); }
+};
 
 __host__ __device__ constexpr int padc(int i) { return i + (i >> 4); }
-template <int NFFT> struct BufLayout { static constexpr int kFloat2 = Plan<NFFT>::N + Plan<NFFT>::N / 16; };
+template <int NFFT> struct BufLayout {
+    static constexpr int kFloat2 = ((Plan<NFFT>::padB(Plan<NFFT>::N - 1) + 2) / 2) * 2;      // padB is the wider of the two
+};
 
 // per-lane twiddle table: stage 1 block [4][32] (k = j mod R0 does not depend on b) then stage 2 block
 // [NB2][4][32], float4 entries holding the forward twiddles (cos, -sin) of r = 2q and r = 2q+1
@@ -86,16 +98,18 @@ template <int DIR> struct Dft<8, DIR> {
 // Per-lane base offsets into the padded buffer (float2 units), computed once per warp.
 //   ld : contiguous accesses  lane + c, c a multiple of 32          -> ld + padc(c)
 //   s0 : stage-0 stores       R0*j + r,  j = lane + 32 b            -> s0 + r + padc(32*R0*b)
-//   s1 : stage-1 stores       (j/R0)*R0*R1 + j%R0 + r*R0            -> s1 + padc(r*R0) + padc(32*R1*b)
+//   s1 : stage-1 stores       (j/R0)*R0*R1 + j%R0 + r*R0            -> s1 + padB(r*R0) + padB(32*R1*b)   (second layout)
+//   ldB: stage-2 loads        lane + c                              -> ldB + padB(c)
 template <int NFFT>
 struct LaneBase {
-    int ld, s0, s1;
+    int ld, ldB, s0, s1;
     __device__ __forceinline__ explicit LaneBase(int lane) {
         using P = Plan<NFFT>;
         ld = padc(lane);
+        ldB = P::padB(lane);
         s0 = padc(P::R0 * lane);
         const int i1 = (lane / P::R0) * P::R0 * P::R1 + (lane % P::R0);
-        s1 = padc(i1);
+        s1 = P::padB(i1);
     }
 };
 
@@ -154,7 +168,7 @@ __device__ __forceinline__ void fft_warp(float2* buf, const float4* __restrict__
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int r = 0; r < R; ++r) buf[lb.s1 + padc(r * P::R0) + padc(32 * R * b)] = v[b][r];
+            for (int r = 0; r < R; ++r) buf[lb.s1 + P::padB(r * P::R0) + P::padB(32 * R * b)] = v[b][r];
     }
     __syncwarp();
     {   // stage 2: Ns = R0*R1 = N/R2, outputs j + r*Ns in natural order
@@ -163,7 +177,7 @@ __device__ __forceinline__ void fft_warp(float2* buf, const float4* __restrict__
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int r = 0; r < R; ++r) v[b][r] = buf[lb.ld + padc(32 * b + r * (N / R))];
+            for (int r = 0; r < R; ++r) v[b][r] = buf[lb.ldB + P::padB(32 * b + r * (N / R))];
         stage_compute<N, R, true, true, DIR>(v, tw + L::kStage1, lane);
         __syncwarp();
 #pragma unroll

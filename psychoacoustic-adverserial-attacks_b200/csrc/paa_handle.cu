@@ -75,14 +75,17 @@ int paa_create(int device, int n_fft, int hop, int sr, paa_handle** out) {
 
     std::vector<float> tw, post;
     if (n_fft == 1024) build_tables<1024>(tw, post); else build_tables<512>(tw, post);
-    h->off_twiddle = round16((size_t)n_fft * 4);
-    h->off_post = round16(h->off_twiddle + tw.size() * 4);
-    h->blob_bytes = round16(h->off_post + post.size() * 4);
+    // blob = [twiddles | split twiddles | window/2]: the first two stay in shared memory for the whole kernel, the
+    // window only passes through (paa_stft.cu)
+    h->off_twiddle = 0;
+    h->off_post = round16(tw.size() * 4);
+    h->off_window = round16(h->off_post + post.size() * 4);
+    h->blob_bytes = round16(h->off_window + (size_t)n_fft * 4);
     std::vector<unsigned char> blob(h->blob_bytes, 0);
     {   // the device table holds w/2 (exact): the real-FFT split then needs no 0.5, and 2/n_fft is folded into the per-bin op
         std::vector<float> half(h->h_window);
         for (float& v : half) v *= 0.5f;
-        std::memcpy(blob.data(), half.data(), (size_t)n_fft * 4);
+        std::memcpy(blob.data() + h->off_window, half.data(), (size_t)n_fft * 4);
     }
     std::memcpy(blob.data() + h->off_twiddle, tw.data(), tw.size() * 4);
     std::memcpy(blob.data() + h->off_post, post.data(), post.size() * 4);

@@ -19,10 +19,10 @@ struct paa_handle {
     int no_coop = 0;         // set if the device refused a cooperative launch: use the three-kernel form
 
     // one device blob, copied into shared memory by a 1-D TMA bulk copy at kernel start:
-    //   [window n_fft f32][twiddles (per-lane, stages 1..2) float2][post twiddles N/2+1 float2]
+    //   [twiddles (per-lane, stages 1..2) float4][split twiddles N/2+1 float2][window/2 n_fft f32]
     void* d_blob = nullptr;
     size_t blob_bytes = 0;
-    size_t off_twiddle = 0, off_post = 0;
+    size_t off_twiddle = 0, off_post = 0, off_window = 0;
     std::vector<float> h_window;
 
     // fletcher_munson penalty grid, frequency axis pre-interpolated per rfft bin

@@ -50,7 +50,7 @@ struct StftArgs {
     int out_len;
     // tables
     const void* blob;
-    unsigned blob_bytes, off_tw, off_post;
+    unsigned blob_bytes, off_tw, off_post, off_win;   // blob = [twiddles | split twiddles | window/2]; [0, off_win) stays resident
     // per-bin op
     float bin_hz, f_min, f_max;
     int k_lo, k_hi;        // min_max_freqs as bin indices: keep k < k_lo or k >= k_hi
@@ -275,13 +275,14 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
 
     // shared-memory carve-up (all offsets multiples of 16 bytes)
     unsigned char* sp = smem;
-    float* s_win = (float*)sp;
     const float4* s_tw = (const float4*)(sp + a.off_tw);
     const float2* s_post = (const float2*)(sp + a.off_post);
-    sp += a.blob_bytes;
+    sp += a.off_win;                           // the window itself only visits shared memory (see below)
     float* s_thr = (float*)sp;                 // per-bin table of the operator: phon limits, or the fletcher_munson blob
     if (OP == OP_PHON || OP == OP_PHON_DB) sp += ((F * 4 + 15) / 16) * 16;
     if (SINK == SINK_REDUCE) sp += a.fm_blob_bytes;
+    float* s_renv = (float*)sp;                // reciprocal window envelope of an interior hop-block
+    if (SINK == SINK_TIME) sp += ((hop * 4 + 15) / 16) * 16;
     float2* s_fft = (float2*)sp;
     sp += (size_t)kWarps * BufLayout<NFFT>::kFloat2 * sizeof(float2);
     float* s_in = (float*)sp;
@@ -296,8 +297,11 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (tid == 0) {
+        // tables stay; the window lands in the (still idle) FFT buffers: every lane copies its 16 values to
+        // registers and the envelope table is derived from it before the first frame overwrites it
         mbar_expect_tx(&bar, a.blob_bytes + (SINK == SINK_REDUCE ? a.fm_blob_bytes : 0u));
-        tma_bulk_g2s(s_win, a.blob, a.blob_bytes, &bar);
+        tma_bulk_g2s(smem, a.blob, a.off_win, &bar);
+        tma_bulk_g2s(s_fft, (const unsigned char*)a.blob + a.off_win, a.blob_bytes - a.off_win, &bar);
         if (SINK == SINK_REDUCE) tma_bulk_g2s(s_thr, a.fm_blob, a.fm_blob_bytes, &bar);
     }
 
@@ -383,19 +387,27 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
         }
     }
     mbar_wait(&bar, 0);
+    // this lane's slice of the (halved) window lives in registers for the whole tile: the first forward stage and the
+    // last inverse stage touch the same points m = lane + 32*j, j = 0 .. N/32-1 (saves 64 smem wavefronts per frame)
+    float2 wreg[N / 32];
+    {
+        const float* s_win = reinterpret_cast<const float*>(s_fft);      // visiting copy, overwritten by the first FFT
+        const float2* win2 = reinterpret_cast<const float2*>(s_win);
+#pragma unroll
+        for (int j = 0; j < N / 32; ++j) wreg[j] = win2[lane + 32 * j];
+        if (SINK == SINK_TIME) {
+            for (int q = tid; q < hop; q += kThreadsStft) {
+                float e = 0.f;
+                for (int d = R - 1; d >= 0; --d) { const float wv = 2.f * s_win[d * hop + q]; e += wv * wv; }
+                s_renv[q] = 1.f / e;
+            }
+        }
+    }
     __syncthreads();
 
     // ---- frames ----------------------------------------------------------------------------------
     float2* buf = s_fft + (size_t)warp * BufLayout<NFFT>::kFloat2;
     const LaneBase<NFFT> lb(lane);
-    // this lane's slice of the (halved) window lives in registers for the whole tile: the first forward stage and the
-    // last inverse stage touch the same points m = lane + 32*j, j = 0 .. N/32-1 (saves 64 smem wavefronts per frame)
-    float2 wreg[N / 32];
-    if (SRC == SRC_TIME || SINK == SINK_TIME) {
-        const float2* win2 = reinterpret_cast<const float2*>(s_win);
-#pragma unroll
-        for (int j = 0; j < N / 32; ++j) wreg[j] = win2[lane + 32 * j];
-    }
     float acc = 0.f;
     for (int r = 0; r < R; ++r) {
         for (int q = 0; q < a.Q; ++q) {
@@ -437,15 +449,9 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     // ---- epilogue -----------------------------------------------------------------------------------
     if (SINK == SINK_TIME) {
         // y[n] = ola[n] / sum_t w^2[n + n/2 - t*hop]  (torch.istft's window envelope), zero past hop*(T'-1).
-        // Interior hop-blocks share one reciprocal envelope table, built in the now idle FFT buffers; the
-        // R-1 blocks at either end of a row see fewer frames and take the slow path.
-        float* s_renv = reinterpret_cast<float*>(s_fft);
-        for (int q = tid; q < hop; q += kThreadsStft) {
-            float e = 0.f;
-            for (int d = R - 1; d >= 0; --d) { const float wv = 2.f * s_win[d * hop + q]; e += wv * wv; }
-            s_renv[q] = 1.f / e;
-        }
-        __syncthreads();
+        // Interior hop-blocks share the reciprocal envelope table built at start-up; the R-1 blocks at either end
+        // of a row see fewer frames and take the slow path (window from global memory).
+        const float* g_win = reinterpret_cast<const float*>((const unsigned char*)a.blob + a.off_win);
         float* yr = a.y + (size_t)row * a.out_len;
         const bool vec = (a.out_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15u) == 0);
         for (int jb = warp; jb < S; jb += kWarps) {
@@ -467,7 +473,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
                             const int t = ub - d;
                             if (t < 0 || t >= a.n_frames) continue;
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) { const float wv = 2.f * s_win[d * hop + q + c]; e[c] += wv * wv; }
+                            for (int c = 0; c < 4; ++c) { const float wv = 2.f * __ldg(g_win + d * hop + q + c); e[c] += wv * wv; }
                         }
                         r = make_float4(1.f / e[0], 1.f / e[1], 1.f / e[2], 1.f / e[3]);
                     }
@@ -605,10 +611,11 @@ __global__ void k_spec_fm_partials(StftArgs a, int F) {
 template <int NFFT>
 size_t smem_bytes(const paa_handle* h, int src, int sink, int op, int FT, int S) {
     constexpr int N = NFFT / 2;
-    size_t b = h->blob_bytes;
+    size_t b = h->off_window;
+    if (sink == SINK_TIME) b += ((h->hop * 4 + 15) / 16) * 16;
     if (op == OP_PHON || op == OP_PHON_DB) b += (((N + 1) * 4 + 15) / 16) * 16;
     if (sink == SINK_REDUCE) b += h->fm_blob_bytes;
-    b += (size_t)kWarps * (N + N / 16) * sizeof(float2);
+    b += (size_t)kWarps * BufLayout<NFFT>::kFloat2 * sizeof(float2);
     if (src == SRC_TIME) b += (size_t)((FT - 1) * h->hop + NFFT) * 4;
     if (sink == SINK_TIME) b += (size_t)S * h->hop * 4;
     return b;
@@ -640,7 +647,7 @@ void fill_common(const paa_handle* h, StftArgs& a, int rows, int T, int n_frames
     a.frames_per_tile = kWarps * a.R * a.Q;
     a.blocks_per_tile = a.frames_per_tile - a.R + 1;
     a.blob = h->d_blob; a.blob_bytes = (unsigned)h->blob_bytes;
-    a.off_tw = (unsigned)h->off_twiddle; a.off_post = (unsigned)h->off_post;
+    a.off_tw = (unsigned)h->off_twiddle; a.off_post = (unsigned)h->off_post; a.off_win = (unsigned)h->off_window;
     a.bin_hz = h->bin_hz;
     a.fm_blob = h->d_fm_blob; a.fm_blob_bytes = (unsigned)h->fm_blob_bytes;
     a.fm_np = h->fm_n_phon; a.fm_uniform = h->fm_uniform; a.fm_fill = h->fm_fill;
