@@ -132,12 +132,27 @@ __device__ __forceinline__ void stage_compute(float2 (&v)[N / R / 32][R], const 
     }
 }
 
+// The same with the twiddles of the stage in registers: stage 1 has k = j mod R0 = lane mod R0 for every b, so one
+// set of R-1 twiddles serves the whole tile (loaded once per warp, 32 shared-memory wavefronts per frame saved).
+template <int N, int R, int DIR>
+__device__ __forceinline__ void stage_compute_reg(float2 (&v)[N / R / 32][R], const float4 (&w)[R / 2]) {
+#pragma unroll
+    for (int b = 0; b < N / R / 32; ++b) {
+#pragma unroll
+        for (int q = 0; q < R / 2; ++q) {
+            if (q > 0) v[b][2 * q] = cmul_tw<DIR>(v[b][2 * q], w[q].x, w[q].y);
+            v[b][2 * q + 1] = cmul_tw<DIR>(v[b][2 * q + 1], w[q].z, w[q].w);
+        }
+        Dft<R, DIR>::run(v[b]);
+    }
+}
+
 // Complex FFT of N points.  First-stage inputs come from `first` (functor (m, c) -> float2) and the
 // result of the last stage is handed to `last` (functor (m, c, float2)) in natural order; m = lane + c
 // with c a compile-time multiple of 32, so callers can address  base(lane) + padc(c).
 template <int NFFT, int DIR, class First, class Last>
-__device__ __forceinline__ void fft_warp(float2* buf, const float4* __restrict__ tw, int lane, const LaneBase<NFFT>& lb,
-                                         First first, Last last) {
+__device__ __forceinline__ void fft_warp(float2* buf, const float4* __restrict__ tw, const float4 (&tw1)[Plan<NFFT>::R1 / 2],
+                                         int lane, const LaneBase<NFFT>& lb, First first, Last last) {
     using P = Plan<NFFT>;
     using L = TwLayout<NFFT>;
     constexpr int N = P::N;
@@ -163,7 +178,7 @@ __device__ __forceinline__ void fft_warp(float2* buf, const float4* __restrict__
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int r = 0; r < R; ++r) v[b][r] = buf[lb.ld + padc(32 * b + r * (N / R))];
-        stage_compute<N, R, true, false, DIR>(v, tw, lane);
+        stage_compute_reg<N, R, DIR>(v, tw1);
         __syncwarp();
 #pragma unroll
         for (int b = 0; b < NB; ++b)

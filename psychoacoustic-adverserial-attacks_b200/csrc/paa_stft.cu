@@ -408,6 +408,9 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     // ---- frames ----------------------------------------------------------------------------------
     float2* buf = s_fft + (size_t)warp * BufLayout<NFFT>::kFloat2;
     const LaneBase<NFFT> lb(lane);
+    float4 tw1[P::R1 / 2];                     // stage-1 twiddles of this lane (same for every butterfly and frame)
+#pragma unroll
+    for (int q = 0; q < P::R1 / 2; ++q) tw1[q] = s_tw[q * 32 + lane];
     float acc = 0.f;
     for (int r = 0; r < R; ++r) {
         for (int q = 0; q < a.Q; ++q) {
@@ -418,7 +421,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
             if (SRC == SRC_TIME) {
                 const float2* x2 = reinterpret_cast<const float2*>(s_in + f * hop);
                 fft_warp<NFFT, -1>(
-                    buf, s_tw, lane, lb,
+                    buf, s_tw, tw1, lane, lb,
                     [&](int m, int c) { const float2 xv = x2[m], wv = wreg[c / 32]; return make_float2(xv.x * wv.x, xv.y * wv.y); },
                     [&](int, int c, float2 v) { buf[lb.ld + padc(c)] = v; });
                 __syncwarp();
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
                 const int obase = (f - R + 1) * hop;                 // owned-region coordinate of frame sample 0
                 const int olim = S * hop;
                 fft_warp<NFFT, +1>(
-                    buf, s_tw, lane, lb, [&](int, int c) { return buf[lb.ld + padc(c)]; },
+                    buf, s_tw, tw1, lane, lb, [&](int, int c) { return buf[lb.ld + padc(c)]; },
                     [&](int m, int c, float2 v) {
                         const int o = obase + 2 * m;
                         if (o >= 0 && o < olim) {
