@@ -1,1 +1,1 @@
-from . import build, parser, sharding, train  # noqa: F401
+from . import build, parser, save, sharding, train  # noqa: F401

@@ -99,3 +99,20 @@ def test_cpu_tensors_are_refused():
     args = paa_b200.training_utils.parser.create_arg_parser().parse_args(["--norm_type", "l2"])
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         paa_b200.perturbation_constraint(torch.zeros(1, 4096), None, args, None, None)
+
+
+def test_checkpoint_formats_roundtrip(tmp_path):
+    """perturbation.pt / results.json as the reference writes them (save.py:155-156, :226-256)."""
+    import json
+    import torch
+    from paa_b200.training_utils import save
+    p = torch.randn(1, 1000)
+    path = tmp_path / "perturbation.pt"
+    save.save_pert(p.requires_grad_(True), str(path))
+    back = torch.load(str(path))                       # plain torch.load, as build.py:294-299 does
+    assert back.dtype == torch.float32 and back.shape == (1, 1000) and not back.requires_grad
+    assert torch.equal(back, p.detach()) and torch.equal(save.load_pert(str(path), "cpu"), p.detach())
+    r = save.save_json_results(str(tmp_path), "snr", 40, epoch=3, test_loss_clean=2.0, test_loss_perturbed=5.0,
+                               skipped=None, per_split={"a": 1.23456})
+    on_disk = json.load(open(tmp_path / "results.json"))
+    assert on_disk == r and r["perturbation_efficiency"] == 2.5 and "skipped" not in r and r["per_split"] == {"a": 1.2346}
