@@ -255,7 +255,6 @@ struct FinalArgs {
     int nblocks;
     float* scalars;
     float eps;           // l2: epsilon; tv: tv_epsilon; snr: snr_db
-    float snr_linear_inv_unused;
     double snr_linear;   // 10**(snr_db/10), python double
     double n_p;          // numel(p)
     double n_clean;      // numel(clean)

@@ -121,6 +121,11 @@ CASES = [
     ("max_phon", 0.03, {}), ("max_phon", 0.1, dict(n_fft=512, win_length=512)),
     ("fletcher_munson", 0.1, {}), ("fletcher_munson", 0.1, dict(fm_epsilon=1e5)),
     ("fletcher_munson", 0.1, dict(n_fft=512, win_length=512, fm_epsilon=0.5)),
+    # other overlaps: R = n_fft/hop = 2 (two frames per warp and phase) and R = 8
+    ("max_phon", 0.05, dict(hop_length=512)), ("min_max_freqs", 0.01, dict(hop_length=512, min_freq_attack=300.0, max_freq_attack=3400.0)),
+    ("fletcher_munson", 0.1, dict(hop_length=512)),
+    ("max_phon", 0.05, dict(hop_length=128)), ("min_max_freqs", 0.01, dict(hop_length=128)), ("fletcher_munson", 0.1, dict(hop_length=128)),
+    ("max_phon", 0.05, dict(n_fft=512, win_length=512, hop_length=64)),
 ]
 
 
@@ -281,3 +286,55 @@ def test_compose_clamp_forward_backward(rows, B, T, env):
         assert torch.equal(pb.grad, pa.grad)                                    # element-wise: bit exact
     else:
         assert rel_max(pb.grad, pa.grad) < 1e-6                                 # batch sum: order of additions only
+
+
+def test_abi_status_codes_on_device(env):
+    """The C ABI's own error conventions (include/paa.h): aliasing, null pointers, missing state, bad shapes."""
+    import ctypes as C
+    from paa_b200 import paa_lib as L
+    h = C.c_void_p()
+    assert L.lib.paa_create(0, 1024, 256, 16000, C.byref(h)) == L.OK
+    try:
+        p = torch.zeros(2, 8000, device="cuda")
+        out = torch.empty_like(p)
+        scratch = torch.empty(L.lib.paa_scratch_bytes(h, 2, 8000), dtype=torch.uint8, device="cuda")
+        st = L.stream_ptr(p.device)
+        assert L.lib.paa_num_bins(h) == 513 and L.lib.paa_num_frames(h, 8000) == 32
+        assert L.lib.paa_project_min_max_freqs(h, p.data_ptr(), p.data_ptr(), 2, 8000, 8000, 120.0, 2e4, None, scratch.data_ptr(), st) == L.ERR_ALIAS
+        assert L.lib.paa_project_fletcher_munson(h, p.data_ptr(), out.data_ptr(), 2, 8000, 8000, 2.0, 1, None, scratch.data_ptr(), st) == L.ERR_STATE
+        assert L.lib.paa_project_snr(h, p.data_ptr(), out.data_ptr(), 2, 8000, None, 0, 40.0, None, scratch.data_ptr(), st) == L.ERR_NEED_CLEAN
+        assert L.lib.paa_project_l2(h, None, out.data_ptr(), 2, 8000, 0.05, None, scratch.data_ptr(), st) == L.ERR_NULL
+        assert L.lib.paa_project_l2(h, p.data_ptr(), out.data_ptr(), 0, 8000, 0.05, None, scratch.data_ptr(), st) == L.ERR_SHAPE
+        assert L.lib.paa_project_max_phon(h, p.data_ptr(), out.data_ptr(), 2, 400, 400, p.data_ptr(), 65.0, None, scratch.data_ptr(), st) == L.ERR_SHAPE
+        bad = L.Step(7, p.data_ptr(), 1e-4, None, None, 0, 0.9, 0.999, 1e-8)
+        assert L.lib.paa_project_linf(h, p.data_ptr(), out.data_ptr(), 2, 8000, -1e-4, 1e-4, C.byref(bad), st) == L.ERR_UNSUPPORTED
+        adam = L.Step(L.STEP_ADAM, p.data_ptr(), 1e-4, None, None, 1, 0.9, 0.999, 1e-8)
+        assert L.lib.paa_project_linf(h, p.data_ptr(), out.data_ptr(), 2, 8000, -1e-4, 1e-4, C.byref(adam), st) == L.ERR_NULL
+        tv = L.Step(L.STEP_PGD, p.data_ptr(), 1e-4, None, None, 0, 0.9, 0.999, 1e-8)
+        assert L.lib.paa_project_tv(h, p.data_ptr(), p.data_ptr(), 2, 8000, p.data_ptr(), 2, 8000, 1e-3, C.byref(tv), scratch.data_ptr(), st) == L.ERR_ALIAS
+        # in place is fine for linf / l2 / snr
+        assert L.lib.paa_project_l2(h, p.data_ptr(), p.data_ptr(), 2, 8000, 0.05, None, scratch.data_ptr(), st) == L.OK
+        torch.cuda.synchronize()
+        n0 = L.lib.paa_launch_count()
+        assert L.lib.paa_project_linf(h, p.data_ptr(), p.data_ptr(), 2, 8000, -1e-4, 1e-4, None, st) == L.OK
+        assert L.lib.paa_launch_count() == n0 + 1
+    finally:
+        assert L.lib.paa_destroy(h) == L.OK
+
+
+def test_in_place_reductions_match_out_of_place(env):
+    from paa_b200 import paa_lib as L
+    g = torch.Generator(device="cuda").manual_seed(11)
+    p = torch.randn(4, 20000, generator=g, device="cuda") * 0.01
+    gr = torch.randn(4, 20000, generator=g, device="cuda")
+    clean = torch.rand(4, 20000, generator=g, device="cuda") * 0.1
+    plan = L.plan_plain(p)
+    step = L.make_step(L.STEP_PGD, gr, 1e-4)
+    out = torch.empty_like(p)
+    st = L.stream_ptr(p.device)
+    L.check(L.lib.paa_project_snr(plan.h, p.data_ptr(), out.data_ptr(), 4, 20000, clean.data_ptr(), clean.numel(), 40.0,
+                                  L.step_ref(step), plan.scratch(4, 20000), st))
+    q = p.clone()
+    L.check(L.lib.paa_project_snr(plan.h, q.data_ptr(), q.data_ptr(), 4, 20000, clean.data_ptr(), clean.numel(), 40.0,
+                                  L.step_ref(step), plan.scratch(4, 20000), st))
+    assert torch.equal(q, out)
