@@ -116,6 +116,7 @@ size_t paa_scratch_bytes(const paa_handle* h, int rows, int T) {
 }
 
 int paa_scalars(const paa_handle* h, const void* scratch, float* out8, void* stream) {
+    PaaDeviceGuard device_guard(h);
     if (!h || !scratch || !out8) return PAA_ERR_NULL;
     PAA_CUDA(h, cudaMemcpyAsync(out8, scratch, PAA_S_COUNT * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     PAA_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
@@ -127,6 +128,7 @@ int paa_scalars(const paa_handle* h, const void* scratch, float* out8, void* str
 // outside the grid's frequency range take fill_value (RegularGridInterpolator, bounds_error=False).
 int paa_set_fm_grid(paa_handle* h, const double* phon_knots, int n_phon, const double* freq_knots, int n_freq,
                     const double* values, double fill_value) {
+    PaaDeviceGuard device_guard(h);
     if (!h || !phon_knots || !freq_knots || !values) return PAA_ERR_NULL;
     if (n_phon < 2 || n_freq < 2 || n_phon > 32) return PAA_ERR_SHAPE;      // table must fit shared memory next to the tile
     for (int i = 1; i < n_phon; ++i) if (!(phon_knots[i] > phon_knots[i - 1])) return PAA_ERR_SHAPE;

@@ -52,6 +52,18 @@ extern long long g_paa_launches;       // bumped by every kernel launch (paa_lau
         PAA_CUDA((h), cudaGetLastError());         \
     } while (0)
 
+// Entry points launch on the handle's device whatever the caller's current device is, and put it back.
+struct PaaDeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit PaaDeviceGuard(const paa_handle* h) {
+        if (h && cudaGetDevice(&prev) == cudaSuccess && prev != h->device) switched = cudaSetDevice(h->device) == cudaSuccess;
+    }
+    ~PaaDeviceGuard() { if (switched) cudaSetDevice(prev); }
+    PaaDeviceGuard(const PaaDeviceGuard&) = delete;
+    PaaDeviceGuard& operator=(const PaaDeviceGuard&) = delete;
+};
+
 // ---- scratch layout (bytes) -----------------------------------------------------------------
 // [0,256)            float scalars[PAA_S_COUNT..]           (PAA_S_* indices)
 // [256, 256+P)       double partials[kMaxBlocks][2]

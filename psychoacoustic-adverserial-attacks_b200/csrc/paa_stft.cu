@@ -628,11 +628,8 @@ template <int NFFT, int SRC, int SINK, int OP>
 int launch(paa_handle* h, StftArgs& a, int grid, cudaStream_t st) {
     size_t smem = smem_bytes<NFFT>(h, SRC, SINK, OP, a.frames_per_tile, a.blocks_per_tile);
     auto kern = k_stft<NFFT, SRC, SINK, OP>;
-    static bool configured = false;       // per instantiation; the attribute is idempotent
-    if (!configured) {
-        PAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    // per launch: the attribute belongs to the (function, device) pair and a process may hold handles on several devices
+    PAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreadsStft, smem, st>>>(a);
     PAA_LAUNCH_CHECK(h);
     return PAA_OK;
@@ -737,6 +734,7 @@ extern "C" {
 
 int paa_project_min_max_freqs(paa_handle* h, const float* p_in, float* p_out, int rows, int T, int out_len,
                               double min_freq, double max_freq, const paa_step* step, void* scratch, void* stream) {
+    PaaDeviceGuard device_guard(h);
     if (!h || !p_in || !p_out) return PAA_ERR_NULL;
     int rc = check_time_shape(h, rows, T);
     if (rc) return rc;
@@ -754,6 +752,7 @@ int paa_project_min_max_freqs(paa_handle* h, const float* p_in, float* p_out, in
 int paa_project_max_phon(paa_handle* h, const float* p_in, float* p_out, int rows, int T, int out_len,
                          const float* spl_thresh_F, double phon_reference_db, const paa_step* step, void* scratch,
                          void* stream) {
+    PaaDeviceGuard device_guard(h);
     if (!h || !p_in || !p_out || !spl_thresh_F) return PAA_ERR_NULL;
     int rc = check_time_shape(h, rows, T);
     if (rc) return rc;
@@ -771,6 +770,7 @@ int paa_project_max_phon(paa_handle* h, const float* p_in, float* p_out, int row
 int paa_project_fletcher_munson(paa_handle* h, const float* p_in, float* p_out, int rows, int T, int out_len,
                                 double fm_epsilon, int exact_roundtrip, const paa_step* step, void* scratch,
                                 void* stream) {
+    PaaDeviceGuard device_guard(h);
     if (!h || !p_in || !p_out || !scratch) return PAA_ERR_NULL;
     if (!h->d_fm_blob) return PAA_ERR_STATE;
     int rc = check_time_shape(h, rows, T);
@@ -814,6 +814,7 @@ int paa_project_fletcher_munson(paa_handle* h, const float* p_in, float* p_out, 
 
 int paa_stft(paa_handle* h, const float* x, int rows, int T, float* spec, int64_t sb, int64_t sf, int64_t stt,
              void* stream) {
+    PaaDeviceGuard device_guard(h);
     if (!h || !x || !spec) return PAA_ERR_NULL;
     int rc = check_time_shape(h, rows, T);
     if (rc) return rc;
@@ -828,6 +829,7 @@ int paa_stft(paa_handle* h, const float* x, int rows, int T, float* spec, int64_
 
 int paa_istft(paa_handle* h, const float* spec, int64_t sb, int64_t sf, int64_t stt, int rows, int n_frames, float* y,
               void* stream) {
+    PaaDeviceGuard device_guard(h);
     if (!h || !spec || !y) return PAA_ERR_NULL;
     if (rows <= 0 || n_frames < 2) return PAA_ERR_SHAPE;
     if (!nola_ok(h, n_frames)) return PAA_ERR_NOLA;
@@ -846,6 +848,7 @@ static int spec_grid(const paa_handle* h, long long n) {
 
 int paa_spec_min_max_freqs(paa_handle* h, const float* spec_in, float* spec_out, int rows, int n_frames, int64_t sb,
                            int64_t sf, int64_t stt, double min_freq, double max_freq, void* stream) {
+    PaaDeviceGuard device_guard(h);
     if (!h || !spec_in || !spec_out) return PAA_ERR_NULL;
     if (rows <= 0 || n_frames <= 0) return PAA_ERR_SHAPE;
     StftArgs a{};
@@ -860,6 +863,7 @@ int paa_spec_min_max_freqs(paa_handle* h, const float* spec_in, float* spec_out,
 
 int paa_spec_phon_level(paa_handle* h, const float* spec_in, float* spec_out, int rows, int n_frames, int64_t sb,
                         int64_t sf, int64_t stt, const float* spl_thresh_F, double phon_reference_db, void* stream) {
+    PaaDeviceGuard device_guard(h);
     if (!h || !spec_in || !spec_out || !spl_thresh_F) return PAA_ERR_NULL;
     if (rows <= 0 || n_frames <= 0) return PAA_ERR_SHAPE;
     StftArgs a{};
@@ -900,11 +904,13 @@ static int spec_fm(paa_handle* h, const float* spec_in, float* spec_out, int row
 
 int paa_spec_fm_norm(paa_handle* h, const float* spec_in, int rows, int n_frames, int64_t sb, int64_t sf, int64_t stt,
                      void* scratch, void* stream) {
+    PaaDeviceGuard device_guard(h);
     return spec_fm(h, spec_in, nullptr, rows, n_frames, sb, sf, stt, 0.0, 0, scratch, (cudaStream_t)stream);
 }
 
 int paa_spec_fm_project(paa_handle* h, const float* spec_in, float* spec_out, int rows, int n_frames, int64_t sb,
                         int64_t sf, int64_t stt, double fm_epsilon, void* scratch, void* stream) {
+    PaaDeviceGuard device_guard(h);
     return spec_fm(h, spec_in, spec_out, rows, n_frames, sb, sf, stt, fm_epsilon, 1, scratch, (cudaStream_t)stream);
 }
 

@@ -711,12 +711,14 @@ int paa_make_step(const paa_step* step, int* mode, StepDev* out) {
 }
 
 int paa_launch_adam_prepass(paa_handle* h, const float* p_in, float* p_out, int64_t n, const StepDev& sd, cudaStream_t st) {
+    PaaDeviceGuard device_guard(h);
     return launch_step_clamp<PAA_STEP_ADAM>(h, p_in, p_out, n, 0.f, 0.f, false, sd, st);
 }
 
 extern "C" {
 
 int paa_step_only(paa_handle* h, const float* p_in, float* p_out, int rows, int T, const paa_step* step, void* stream) {
+    PaaDeviceGuard device_guard(h);
     if (!h || !p_in || !p_out) return PAA_ERR_NULL;
     if (rows <= 0 || T <= 0) return PAA_ERR_SHAPE;
     int mode = 0;
@@ -734,6 +736,7 @@ int paa_step_only(paa_handle* h, const float* p_in, float* p_out, int rows, int 
 
 int paa_project_linf(paa_handle* h, const float* p_in, float* p_out, int rows, int T, double lo, double hi,
                      const paa_step* step, void* stream) {
+    PaaDeviceGuard device_guard(h);
     if (!h || !p_in || !p_out) return PAA_ERR_NULL;
     if (rows <= 0 || T <= 0) return PAA_ERR_SHAPE;
     int mode = 0;
@@ -751,18 +754,21 @@ int paa_project_linf(paa_handle* h, const float* p_in, float* p_out, int rows, i
 
 int paa_project_l2(paa_handle* h, const float* p_in, float* p_out, int rows, int T, double epsilon,
                    const paa_step* step, void* scratch, void* stream) {
+    PaaDeviceGuard device_guard(h);
     return project_reduce<NORM_L2>(h, p_in, p_out, rows, T, nullptr, 0, 1, (float)epsilon, 0.0, step, scratch,
                                    (cudaStream_t)stream);
 }
 
 int paa_project_snr(paa_handle* h, const float* p_in, float* p_out, int rows, int T, const float* clean,
                     int64_t clean_numel, double snr_db, const paa_step* step, void* scratch, void* stream) {
+    PaaDeviceGuard device_guard(h);
     return project_reduce<NORM_SNR>(h, p_in, p_out, rows, T, clean, clean_numel, 1, (float)snr_db,
                                     std::pow(10.0, snr_db / 10.0), step, scratch, (cudaStream_t)stream);
 }
 
 int paa_project_tv(paa_handle* h, const float* p_in, float* p_out, int rows, int T, const float* clean,
                    int clean_rows, int clean_T, double tv_epsilon, const paa_step* step, void* scratch, void* stream) {
+    PaaDeviceGuard device_guard(h);
     return project_reduce<NORM_TV>(h, p_in, p_out, rows, T, clean, (int64_t)clean_rows * clean_T, clean_T,
                                    (float)tv_epsilon, 0.0, step, scratch, (cudaStream_t)stream);
 }
@@ -776,6 +782,7 @@ static dim3 compose_grid(const paa_handle* h, int cols, int rows, bool row_paral
 
 int paa_compose_clamp(paa_handle* h, const float* clean, int clean_rows, const float* p, int p_rows, int T,
                       float* x_adv, void* stream) {
+    PaaDeviceGuard device_guard(h);
     if (!h || !clean || !p || !x_adv) return PAA_ERR_NULL;
     if (clean_rows <= 0 || T <= 0 || (p_rows != 1 && p_rows != clean_rows)) return PAA_ERR_SHAPE;
     const bool vec = aligned16(clean) && aligned16(p) && aligned16(x_adv) && (T % 4 == 0);
@@ -788,6 +795,7 @@ int paa_compose_clamp(paa_handle* h, const float* clean, int clean_rows, const f
 
 int paa_compose_clamp_backward(paa_handle* h, const float* clean, int clean_rows, const float* p, int p_rows, int T,
                                const float* grad_x_adv, float* grad_p, void* stream) {
+    PaaDeviceGuard device_guard(h);
     if (!h || !clean || !p || !grad_x_adv || !grad_p) return PAA_ERR_NULL;
     if (clean_rows <= 0 || T <= 0 || (p_rows != 1 && p_rows != clean_rows)) return PAA_ERR_SHAPE;
     const bool vec = aligned16(clean) && aligned16(p) && aligned16(grad_x_adv) && aligned16(grad_p) && (T % 4 == 0);
