@@ -71,7 +71,11 @@ class WerMetric:
 
 def compute_wer(logits, target_texts, processor, wer_metric):
     """argmax -> CTC decode -> WER against the cleaned references (loss_helpers.py:25-32)."""
-    pred_ids = torch.argmax(logits, dim=-1)
+    return wer_from_ids(torch.argmax(logits, dim=-1), target_texts, processor, wer_metric)
+
+
+def wer_from_ids(pred_ids, target_texts, processor, wer_metric):
+    """The decode + WER half of compute_wer, for greedy ids that were kept on the device until the epoch ended."""
     if processor is None:
         pred_texts = greedy_decode(pred_ids)
     else:

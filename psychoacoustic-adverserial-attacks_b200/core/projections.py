@@ -17,6 +17,11 @@ def _rows(p):
     return p.numel() // T, T
 
 
+def _empty(p):
+    """An empty perturbation has nothing to project: torch returns it unchanged (clamp / `norm > eps` is False)."""
+    return p.numel() == 0
+
+
 def project_snr(clean, perturbation, snr_db, _step=None):
     """Rescale so that SNR(clean, perturbation) >= snr_db (projections.py:11-35; the target norm uses
     clean.numel() whatever the shape of the perturbation)."""
@@ -33,6 +38,8 @@ def project_snr(clean, perturbation, snr_db, _step=None):
 def project_linf(p, min_val, max_val, _step=None):
     """clamp(p, min_val, max_val) (projections.py:37-39)."""
     L.need_cuda(p)
+    if _empty(p):
+        return p.detach().clone()
     x = L.f32c(p.detach())
     plan = L.plan_plain(x)
     rows, T = _rows(x)
@@ -45,6 +52,8 @@ def project_linf(p, min_val, max_val, _step=None):
 def project_l2(p, epsilon, _step=None):
     """p * (epsilon/||p||) when ||p|| > epsilon, the norm taken over the whole tensor (projections.py:41-46)."""
     L.need_cuda(p)
+    if _empty(p):
+        return p.detach().clone()
     x = L.f32c(p.detach())
     plan = L.plan_plain(x)
     rows, T = _rows(x)

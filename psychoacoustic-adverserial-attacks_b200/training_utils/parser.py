@@ -34,4 +34,6 @@ def create_arg_parser():
     p.add_argument("--fm_identity_roundtrip", action="store_true")
     # not in the reference: x_adv = clamp(clean + p) and its backward as libpaa kernels instead of autograd's passes
     p.add_argument("--fused_compose", action="store_true")
+    # not in the reference: keep loss / greedy ids on the device and decode them after the epoch (no per-step host sync)
+    p.add_argument("--defer_metrics", action="store_true")
     return p

@@ -130,6 +130,8 @@ def train_epoch(args, train_data_loader, p, model, epoch, processor, interp, wer
     except ImportError:
         from core import loss_helpers
     ctc_scores, wer_scores, times = [], [], []
+    defer = bool(getattr(args, "defer_metrics", False))     # not in the reference: no host sync inside the loop
+    pending = []
     model.eval()
     logger.info("timestamp: %s | starting epoch: %d", datetime.now(), epoch)
     direction = +1 if args.attack_mode == "untargeted" else -1
@@ -147,11 +149,15 @@ def train_epoch(args, train_data_loader, p, model, epoch, processor, interp, wer
             perturbed = (clean_audio + p).clamp_(-1.0, 1.0)
         loss, logits = loss_helpers.get_loss_for_training(model=model, data=perturbed, target_texts=target_texts,
                                                           processor=processor, args=args)
-        ctc_scores.append(float(loss.item()))
-        with torch.inference_mode():
-            wer = loss_helpers.compute_wer(logits=logits, target_texts=target_texts, processor=processor,
-                                           wer_metric=wer_metric)
-        wer_scores.append(float(wer))
+        if defer:
+            # keep the loss and the greedy ids on the device; one synchronisation at the end of the epoch
+            pending.append((loss.detach(), logits.detach().argmax(-1), target_texts))
+        else:
+            ctc_scores.append(float(loss.item()))
+            with torch.inference_mode():
+                wer = loss_helpers.compute_wer(logits=logits, target_texts=target_texts, processor=processor,
+                                               wer_metric=wer_metric)
+            wer_scores.append(float(wer))
 
         if args.optimizer_type == "pgd":
             (direction * loss).backward()
@@ -167,4 +173,7 @@ def train_epoch(args, train_data_loader, p, model, epoch, processor, interp, wer
             raise NotImplementedError(f"Optimization type not implemented: {args.optimizer_type!r}")
         times.append(time.perf_counter() - t0)
 
+    for loss_t, ids_t, texts in pending:                       # same numbers, computed after the last step was enqueued
+        ctc_scores.append(float(loss_t.item()))
+        wer_scores.append(float(loss_helpers.wer_from_ids(ids_t, texts, processor, wer_metric)))
     return TrainEpochResult(p=p, avg_ctc=_avg(ctc_scores), avg_wer=_avg(wer_scores))

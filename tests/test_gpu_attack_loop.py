@@ -69,3 +69,27 @@ def test_train_epoch_runs_and_constrains(norm, opt):
         scheduler.step()                                    # StepLR keeps working on the drop-in optimiser
         sd = optimizer.state_dict()
         assert sd["state"][0]["exp_avg"].shape == (1, T)
+
+
+def test_deferred_metrics_equal_synchronous():
+    """--defer_metrics changes when the loss and WER are read back, not what they are."""
+    import paa_b200  # noqa: F401
+    from paa_b200.core import loss_helpers
+    from paa_b200.training_utils import build, parser, train
+    dev = torch.device("cuda:0")
+    model = tiny_model(dev)
+    for q in model.parameters():
+        q.requires_grad_(False)
+    g = torch.Generator().manual_seed(4)
+    loader = [((torch.rand(2, 16000, generator=g) * 2 - 1) * 0.1, ["hello world this is a test"] * 2) for _ in range(3)]
+    out = []
+    for defer in (False, True):
+        args = parser.create_arg_parser().parse_args(["--norm_type", "linf", "--optimizer_type", "pgd", "--linf_size", "0.002",
+                                                      "--lr", "1e-3"] + (["--defer_metrics"] if defer else []))
+        args.device = str(dev)
+        torch.manual_seed(1)
+        p = build.init_perturbation(args, 16000, None, None, None)
+        wer = loss_helpers.WerMetric()
+        res = train.train_epoch(args, loader, p, model, 0, None, None, wer, None, None)
+        out.append((res.p.detach().clone(), res.avg_ctc, res.avg_wer, wer.errors, wer.words))
+    assert torch.equal(out[0][0], out[1][0]) and out[0][1:] == out[1][1:]

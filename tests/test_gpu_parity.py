@@ -338,3 +338,19 @@ def test_in_place_reductions_match_out_of_place(env):
     L.check(L.lib.paa_project_snr(plan.h, q.data_ptr(), q.data_ptr(), 4, 20000, clean.data_ptr(), clean.numel(), 40.0,
                                   L.step_ref(step), plan.scratch(4, 20000), st))
     assert torch.equal(q, out)
+
+
+def test_empty_and_tiny_inputs(env):
+    """Empty perturbations come back unchanged (torch: clamp of nothing, norm 0 <= eps); one-sample rows work."""
+    paa, orc = env["paa"], env["orc"]
+    for norm in ("linf", "l2"):
+        args = make_args(orc.Hyper(norm_type=norm))
+        e = torch.empty(0, 16, device="cuda")
+        out = paa.perturbation_constraint(e, None, args, None, None)
+        assert out.shape == e.shape
+    args = make_args(orc.Hyper(norm_type="l2", l2_size=0.5))
+    one = torch.tensor([[2.0]], device="cuda")
+    assert abs(float(paa.perturbation_constraint(one, None, args, None, None)) - 0.5) < 1e-6
+    args = make_args(orc.Hyper(norm_type="tv"))
+    col = torch.rand(3, 1, device="cuda")              # T = 1: no neighbours, TV = 0, nothing to scale
+    assert torch.equal(paa.perturbation_constraint(col, col, args, None, None), col)
