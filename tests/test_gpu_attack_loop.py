@@ -93,3 +93,33 @@ def test_deferred_metrics_equal_synchronous():
         res = train.train_epoch(args, loader, p, model, 0, None, None, wer, None, None)
         out.append((res.p.detach().clone(), res.avg_ctc, res.avg_wer, wer.errors, wer.words))
     assert torch.equal(out[0][0], out[1][0]) and out[0][1:] == out[1][1:]
+
+
+@pytest.mark.parametrize("norm", ["snr", "max_phon", "linf"])
+def test_cuda_graph_capture(norm):
+    """The fused step + projection makes no host synchronisation and allocates nothing itself, so it can be captured
+    in a CUDA graph -- including the cooperative launch of the reducing norms."""
+    import paa_b200
+    from paa_b200.training_utils import build, parser
+    dev = torch.device("cuda:0")
+    args = parser.create_arg_parser().parse_args(["--norm_type", norm, "--optimizer_type", "pgd", "--snr_db", "40"])
+    args.device = str(dev)
+    g = torch.Generator(device=dev).manual_seed(2)
+    clean = (torch.rand(4, 16000, generator=g, device=dev) * 2 - 1) * 0.1
+    p = torch.randn(4, 16000, generator=g, device=dev) * 0.02
+    grad = torch.randn(4, 16000, generator=g, device=dev)
+    thr = build.init_phon_threshold_tensor(args)
+    want = paa_b200.step_and_project(p, grad, clean, args, None, thr)          # also warms handle, scratch, attributes
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = paa_b200.step_and_project(p, grad, clean, args, None, thr)
+    for _ in range(3):
+        out.zero_()
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    grad.neg_()                                                                 # replays read the live input buffers
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, paa_b200.step_and_project(p, grad, clean, args, None, thr))
