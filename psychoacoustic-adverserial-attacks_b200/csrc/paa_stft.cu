@@ -161,23 +161,27 @@ __device__ __forceinline__ void op_phon(const float* lim_c, int k, float c, floa
 // `tab` is the fm blob (global memory for the element-wise kernel, shared memory in the fused kernel).
 template <bool FAST>
 __device__ __forceinline__ float fm_term(const StftArgs& a, const float* __restrict__ tab, int F, int k, float re, float im) {
-    const float m = sqrtf(fmaf(re, re, im * im));
-    const float P = m * m;
+    // torch: power = abs(X)**2 (a square root and a square); FAST keeps re^2+im^2, one rounding away from it
+    const float P = FAST ? fmaf(re, re, im * im) : [&] { const float m = sqrtf(fmaf(re, re, im * im)); return m * m; }();
     // FAST: MUFU.LG2 (abs error ~1e-6 dB, it only positions the query inside a 10 dB cell)
     const float spl = FAST ? 3.0102999566398120f * __log2f(P + 1e-10f) : 10.f * log10f(P + 1e-10f);
     float w = a.fm_fill;
     if (!(spl < a.fm_k0) && !(spl > a.fm_klast)) {       // bins outside the frequency axis hold `fill` in every row
         int i;
+        float tp;
         if (a.fm_uniform) {
-            i = (int)((spl - a.fm_k0) * a.fm_inv_dk);
+            // equally spaced phon knots (the reference's 0,10,..,90): cell and fraction by arithmetic, no table reads
+            const float t = (spl - a.fm_k0) * a.fm_inv_dk;
+            i = max(0, min((int)t, a.fm_np - 2));
+            tp = t - (float)i;
         } else {
             i = 0;
             for (int q = 1; q < a.fm_np - 1; ++q) i += (spl > tab[q]) ? 1 : 0;
+            i = max(0, min(i, a.fm_np - 2));
+            const float k0 = tab[i], k1 = tab[i + 1];
+            tp = FAST ? __fdividef(spl - k0, k1 - k0) : (spl - k0) / (k1 - k0);
         }
-        i = max(0, min(i, a.fm_np - 2));
-        const float k0 = tab[i], k1 = tab[i + 1];
         const float c0 = tab[64 + i * F + k], c1 = tab[64 + (i + 1) * F + k];
-        const float tp = FAST ? __fdividef(spl - k0, k1 - k0) : (spl - k0) / (k1 - k0);
         w = fmaf(tp, c1 - c0, c0);
     }
     return P * w;
