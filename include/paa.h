@@ -112,7 +112,15 @@ int paa_project_tv(paa_handle* h, const float* p_in, float* p_out, int rows, int
 /* ---- step + projection, STFT domain (train.py:38-66): STFT -> per-bin op -> ISTFT in ONE kernel,
  * the spectrum never reaches HBM.  p_out must NOT alias p_in.  p_out is [rows, out_len]; samples
  * past hop*(T'-1) are zero (train.py:27-35 with clean_audio given: out_len = clean.shape[-1];
- * with clean_audio=None pass out_len = hop*(T'-1)). */
+ * with clean_audio=None pass out_len = hop*(T'-1)).
+ * A PGD step is applied while the input span is staged; an Adam step runs first as a streaming pass into
+ * scratch (halo samples are recomputed by neighbouring tiles, optimiser state must be updated once).
+ * max_phon: spl_thresh_F is the device array build.py:325-348 makes (F floats); the fused kernel clips in the
+ * linear domain, |X'| = min(|X| + 1e-8, 10^(thr/20)), which equals the reference's dB round trip up to its own
+ * fp32 rounding (~1e-6 relative); paa_spec_phon_level below performs the literal dB round trip.
+ * fletcher_munson needs paa_set_fm_grid first (PAA_ERR_STATE otherwise) and is two passes: norm, then
+ * exact_roundtrip != 0: ISTFT(scale * STFT(q)) as the reference computes it;
+ * exact_roundtrip == 0: scale * q on the reconstructed span (the same thing algebraically, 8 B/sample). */
 int paa_project_min_max_freqs(paa_handle* h, const float* p_in, float* p_out, int rows, int T, int out_len,
                               double min_freq, double max_freq,
                               const paa_step* step, void* scratch, void* stream);              /* projections.py:68-80 */
