@@ -67,12 +67,13 @@ __device__ __forceinline__ float stepped1(const float* p, int64_t i, const StepD
 
 // The same in two halves, so that the loads of the next float4 can be issued before the arithmetic on the
 // current one (software pipelining in k_fused: memory-level parallelism, not instruction count, bounds it).
-struct Raw4 { float4 p, g, m, v; };
+struct Raw4 { float4 p, g, m, v; float np, ng; };      // np/ng: the element after the float4 (tv, last lane only)
 template <int STEP>
 __device__ __forceinline__ Raw4 load_raw4(const float* p, int64_t i, const StepDev& s) {
     Raw4 r;
     r.p = ld4(p + i);
     r.g = r.m = r.v = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.np = r.ng = 0.f;
     if (STEP != PAA_STEP_NONE) r.g = ld4(s.grad + i);
     if (STEP == PAA_STEP_ADAM) { r.m = ld4(s.m + i); r.v = ld4(s.v + i); }
     return r;
@@ -380,7 +381,10 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
             if (act) x = finish4<STEP, false>(raw, i, s);
             float nx = __shfl_down_sync(0xffffffffu, x.x, 1);
             const bool has_next = act && (i + 4 < a.n);
-            if (has_next && (lane == 31 || i4 + 1 >= n4)) nx = stepped1<STEP, false>(a.p_in, i + 4, s);
+            if (has_next && (lane == 31 || i4 + 1 >= n4)) {       // its operands came with the float4 (fetch)
+                float m1 = 0.f, v1 = 0.f;
+                nx = step_one<STEP == PAA_STEP_ADAM ? PAA_STEP_NONE : STEP>(raw.np, raw.ng, m1, v1, s);
+            }
             if (act) acc0 += tv_quad(x, nx, colp, a.T, has_next);
             colp += stepp;
             if (colp >= a.T) colp -= a.T;
@@ -390,7 +394,12 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     auto fetch = [&](int64_t i4, bool act) -> Raw4 {
         Raw4 r;
         r.p = r.g = r.m = r.v = make_float4(0.f, 0.f, 0.f, 0.f);
+        r.np = r.ng = 0.f;
         if (act) r = load_raw4<STEP>(a.p_in, i4 * 4, s);
+        if (NORM == NORM_TV && act && (lane == 31 || i4 + 1 >= n4) && i4 * 4 + 4 < a.n) {
+            r.np = a.p_in[i4 * 4 + 4];
+            if (STEP != PAA_STEP_NONE) r.ng = s.grad[i4 * 4 + 4];
+        }
         return r;
     };
 
@@ -449,10 +458,13 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
             const bool act = i4 < c4;
             const int64_t i = i4 * 4;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (act) x = ld4_stream(a.clean + i);
-            float nx = __shfl_down_sync(0xffffffffu, x.x, 1);
             const bool has_next = act && (i + 4 < a.clean_n);
-            if (has_next && (lane == 31 || i4 + 1 >= c4)) nx = a.clean[i + 4];
+            const bool from_mem = has_next && (lane == 31 || i4 + 1 >= c4);
+            float nxl = 0.f;
+            if (act) x = ld4_stream(a.clean + i);
+            if (from_mem) nxl = a.clean[i + 4];                 // issued together with the float4, not after the shuffle
+            float nx = __shfl_down_sync(0xffffffffu, x.x, 1);
+            if (from_mem) nx = nxl;
             if (act) acc1 += tv_quad(x, nx, colc, Tc, has_next);
             colc += stepc;
             if (colc >= Tc) colc -= Tc;
