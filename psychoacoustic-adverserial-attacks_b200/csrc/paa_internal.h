@@ -16,6 +16,7 @@ struct paa_handle {
     int num_sms = 148;
     float bin_hz = 0.f;      // fp32(1/(n_fft*(1/sr))): what torch.fft.rfftfreq multiplies arange by
     mutable int last_cuda_error = 0;
+    mutable int nola_frames = -1, nola_result = 0;   // last window-envelope check (paa_stft.cu: nola_ok)
     int no_coop = 0;         // set if the device refused a cooperative launch: use the three-kernel form
 
     // one device blob, copied into shared memory by a 1-D TMA bulk copy at kernel start:

@@ -670,8 +670,18 @@ void set_band(const paa_handle* h, StftArgs& a, double min_freq, double max_freq
     a.k_lo = lo; a.k_hi = hi;
 }
 
+bool nola_check(const paa_handle* h, int n_frames);
 // torch.istft refuses windows whose overlap-add envelope (after trimming n_fft/2) falls below 1e-11
 bool nola_ok(const paa_handle* h, int n_frames) {
+    // memoised per handle: an attack calls with the same length every step (benign race: same answer from any thread)
+    if (h->nola_frames == n_frames) return h->nola_result != 0;
+    const bool ok = nola_check(h, n_frames);
+    h->nola_result = ok ? 1 : 0;
+    h->nola_frames = n_frames;
+    return ok;
+}
+
+bool nola_check(const paa_handle* h, int n_frames) {
     const int n = h->n_fft, hop = h->hop;
     const long long valid = (long long)hop * (n_frames - 1);
     auto env_at = [&](long long pos) {
