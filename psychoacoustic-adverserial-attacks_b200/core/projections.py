@@ -31,7 +31,7 @@ def project_snr(clean, perturbation, snr_db, _step=None):
     rows, T = _rows(p)
     out = torch.empty_like(p)
     L.check(L.lib.paa_project_snr(plan.h, p.data_ptr(), out.data_ptr(), rows, T, c.data_ptr(), c.numel(), float(snr_db),
-                                  L.step_ref(_step), plan.scratch(rows, T), L.stream_ptr(p.device)), plan.h)
+                                  L.step_ref(_step), plan.scratch(0, 0), L.stream_ptr(p.device)), plan.h)
     return out
 
 
@@ -59,7 +59,7 @@ def project_l2(p, epsilon, _step=None):
     rows, T = _rows(x)
     out = torch.empty_like(x)
     L.check(L.lib.paa_project_l2(plan.h, x.data_ptr(), out.data_ptr(), rows, T, float(epsilon), L.step_ref(_step),
-                                 plan.scratch(rows, T), L.stream_ptr(x.device)), plan.h)
+                                 plan.scratch(0, 0), L.stream_ptr(x.device)), plan.h)
     return out
 
 
@@ -73,7 +73,7 @@ def project_tv(p, args, clean_audio, _step=None):
     rows, T = x.shape
     out = torch.empty_like(x)
     L.check(L.lib.paa_project_tv(plan.h, x.data_ptr(), out.data_ptr(), rows, T, c.data_ptr(), c.shape[0], c.shape[1],
-                                 float(args.tv_epsilon), L.step_ref(_step), plan.scratch(rows, T),
+                                 float(args.tv_epsilon), L.step_ref(_step), plan.scratch(0, 0),
                                  L.stream_ptr(x.device)), plan.h)
     return out
 
@@ -107,7 +107,7 @@ def compute_fm_weighted_norm_interp(stft_p, interp, args):
     plan.set_fm_grid(interp)
     B, F, Tn = s.shape
     sb, sf, st = s.stride()
-    scratch = plan.scratch(B, max(Tn, 1))
+    scratch = plan.scratch(0, 0)
     L.check(L.lib.paa_spec_fm_norm(plan.h, s.data_ptr(), B, Tn, sb, sf, st, scratch, L.stream_ptr(s.device)), plan.h)
     return plan._scratch[:16].view(torch.float32)[L.S_NORM].clone()
 
@@ -122,7 +122,7 @@ def project_fm_norm(stft_p, args, interp):
         s = s.contiguous(); out = torch.empty_like(s)
     B, F, Tn = s.shape
     sb, sf, st = s.stride()
-    scratch = plan.scratch(B, max(Tn, 1))
+    scratch = plan.scratch(0, 0)
     L.check(L.lib.paa_spec_fm_project(plan.h, s.data_ptr(), out.data_ptr(), B, Tn, sb, sf, st, float(args.fm_epsilon),
                                       scratch, L.stream_ptr(s.device)), plan.h)
     return out

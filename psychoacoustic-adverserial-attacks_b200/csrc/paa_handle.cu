@@ -111,7 +111,8 @@ int paa_num_bins(const paa_handle* h) { return h ? h->F : 0; }
 int paa_num_frames(const paa_handle* h, int T) { return (h && T >= 0) ? 1 + T / h->hop : 0; }
 
 size_t paa_scratch_bytes(const paa_handle* h, int rows, int T) {
-    if (!h || rows <= 0 || T <= 0) return 0;
+    if (!h || rows < 0 || T < 0) return 0;
+    // scalars + block partials always; the [rows, T] staging buffer only for the STFT-domain projections
     return (size_t)kScalarBytes + kPartialBytes + (size_t)rows * (size_t)T * sizeof(float) + 256;
 }
 

@@ -116,3 +116,26 @@ def test_checkpoint_formats_roundtrip(tmp_path):
                                skipped=None, per_split={"a": 1.23456})
     on_disk = json.load(open(tmp_path / "results.json"))
     assert on_disk == r and r["perturbation_efficiency"] == 2.5 and "skipped" not in r and r["per_split"] == {"a": 1.2346}
+
+
+def test_host_tables_against_scipy_directly():
+    """Independent of the golden files: libpaa's PCHIP contour and bilinear lookup against scipy's own classes on
+    random queries (the reference builds its tables with exactly these two, iso.py:113-124 and :261-266)."""
+    interpolate = pytest.importorskip("scipy.interpolate")
+    rng = np.random.default_rng(3)
+    ph, fk, w = L.weight_grid()
+    rgi = interpolate.RegularGridInterpolator((ph, fk), w, bounds_error=False, fill_value=1.0)
+    q = np.stack([rng.uniform(-20, 110, 5000), np.exp(rng.uniform(np.log(2), np.log(40000), 5000))], 1)
+    q[:50, 0] = rng.choice(ph, 50)                       # exactly on phon knots
+    q[50:100, 1] = rng.choice(fk, 50)                    # exactly on frequency knots
+    assert np.abs(L.interp2(ph, fk, w, 1.0, q) - rgi(q)).max() < 1e-12
+    # the contour itself: PCHIP of the three ISO tables with the wrapped 20 kHz knot, then the closed form
+    from oracle import paa_oracle as orc
+    f = np.exp(rng.uniform(np.log(20), np.log(20000), 2000))
+    xk = np.concatenate([orc.ISO_BAND_HZ, [20000.0]])
+    al, lu, tf = (interpolate.PchipInterpolator(xk, np.concatenate([t, t[:1]]))(f) for t in (orc.ISO_ALPHA, orc.ISO_LU, orc.ISO_TF))
+    for phon in (0.0, 13.7, 55.0, 90.0):
+        a = 0.00447 * (10.0 ** (0.025 * phon) - 1.15)
+        want = (10.0 / al) * np.log10(a + (0.4 * 10.0 ** ((tf + lu) / 10.0 - 9.0)) ** al) - lu + 94.0
+        assert np.abs(L.iso226_spl(phon, f) - want).max() < 1e-9
+        assert np.abs(orc.iso226_spl(phon, f) - want).max() < 1e-9

@@ -354,3 +354,26 @@ def test_empty_and_tiny_inputs(env):
     args = make_args(orc.Hyper(norm_type="tv"))
     col = torch.rand(3, 1, device="cuda")              # T = 1: no neighbours, TV = 0, nothing to scale
     assert torch.equal(paa.perturbation_constraint(col, col, args, None, None), col)
+
+
+def test_more_than_2g_elements(env):
+    """64-bit indexing: a perturbation with more than 2^31 elements through linf and l2 (properties only)."""
+    from paa_b200 import paa_lib as L
+    paa, orc = env["paa"], env["orc"]
+    rows, T = 2100, 1024 * 1024                    # 2.2e9 elements, 8.8 GB per tensor
+    if torch.cuda.mem_get_info()[0] < 40 * 2**30:
+        pytest.skip("needs ~30 GB of free device memory")
+    p = torch.empty(rows, T, device="cuda").uniform_(-1.0, 1.0)
+    g = torch.empty(rows, T, device="cuda").uniform_(-1.0, 1.0)
+    assert p.numel() > 2**31
+    args = make_args(orc.Hyper(norm_type="linf", optimizer_type="pgd", lr=0.25, linf_size=0.5))
+    out = paa.step_and_project(p, g, None, args, None, None)
+    for sl in (slice(0, 3), slice(rows - 3, rows)):     # both ends of the 64-bit index range
+        assert torch.equal(out[sl], (p[sl] + 0.25 * g[sl].sign()).clamp(-0.5, 0.5))
+    del out
+    args = make_args(orc.Hyper(norm_type="l2", l2_size=100.0))
+    out = paa.perturbation_constraint(p, None, args, None, None)
+    want = float(torch.linalg.vector_norm(p.view(-1)[:2**30].double()) ** 2 + torch.linalg.vector_norm(p.view(-1)[2**30:].double()) ** 2) ** 0.5
+    s = L.plan_plain(p).scalars()
+    assert abs(s[L.S_NORM] / want - 1) < 1e-5 and abs(s[L.S_SCALE] * want / 100.0 - 1) < 1e-5
+    assert abs(float(torch.linalg.vector_norm(out[-7:].double())) / float(torch.linalg.vector_norm(p[-7:].double())) * want / 100.0 - 1) < 1e-5
