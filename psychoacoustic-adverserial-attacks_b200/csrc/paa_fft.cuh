@@ -45,54 +45,68 @@ template <int NFFT> struct TwLayout {
     static constexpr int kTotal = kStage1 + kStage2;
 };
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-// multiply by w (forward, DIR=-1) or conj(w) (inverse, DIR=+1); tables hold forward twiddles (cos, -sin)
+// ---- packed complex arithmetic -------------------------------------------------------------------
+// A complex value is one 64-bit register pair (re, im).  sm_100a has packed fp32 instructions (FADD2 / FMUL2 / FFMA2,
+// PTX add/mul/fma.rn.f32x2) whose operands take a half swap, per-half negation and scalar broadcast for free, so a
+// complex add, a +-i rotation folded into an add, or half a twiddle multiply is ONE issue slot instead of two
+// (same IEEE roundings as the scalar forms; tools/micro/f32x2_bench.cu: same lane throughput, half the issue).
+// The pk()/up() repacks below never cost an instruction when they feed a packed op: ptxas folds them into the
+// operand modifiers (.LO_HI, .NP, .F32).
+typedef unsigned long long cpx;
+__device__ __forceinline__ cpx pk(float x, float y) { cpx r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ void up(cpx v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ float cre(cpx v) { float x, y; up(v, x, y); return x; }
+__device__ __forceinline__ float cim(cpx v) { float x, y; up(v, x, y); return y; }
+__device__ __forceinline__ cpx add2(cpx a, cpx b) { cpx r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ cpx sub2(cpx a, cpx b) { cpx r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ cpx mul2(cpx a, cpx b) { cpx r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ cpx fma2(cpx a, cpx b, cpx c) { cpx r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ cpx bcast(float s) { return pk(s, s); }
+__device__ __forceinline__ cpx conj2(cpx v) { float x, y; up(v, x, y); return pk(x, -y); }
+__device__ __forceinline__ cpx swap2(cpx v) { float x, y; up(v, x, y); return pk(y, x); }
+__device__ __forceinline__ cpx neg2(cpx v) { float x, y; up(v, x, y); return pk(-x, -y); }
+// multiply by -i (DIR < 0, the forward transform's rotation) / +i (DIR > 0)
 template <int DIR>
-__device__ __forceinline__ float2 cmul_tw(float2 v, float wx, float wy) {
-    if (DIR < 0) return make_float2(v.x * wx - v.y * wy, v.x * wy + v.y * wx);
-    return make_float2(v.x * wx + v.y * wy, v.y * wx - v.x * wy);
+__device__ __forceinline__ cpx rot90(cpx v) {
+    float x, y;
+    up(v, x, y);
+    return DIR < 0 ? pk(y, -x) : pk(-y, x);
 }
-// multiply by -i (forward) / +i (inverse)
+// multiply by w (forward, DIR=-1) or conj(w) (inverse, DIR=+1); tables hold forward twiddles (cos, -sin):
+//   forward (vx wx - vy wy, vx wy + vy wx) = v*wx + (+i v)*wy,   inverse (vx wx + vy wy, vy wx - vx wy) = v*wx + (-i v)*wy
 template <int DIR>
-__device__ __forceinline__ float2 rot90(float2 v) {
-    return DIR < 0 ? make_float2(v.y, -v.x) : make_float2(-v.y, v.x);
+__device__ __forceinline__ cpx cmul_tw(cpx v, float wx, float wy) {
+    return fma2(rot90<-DIR>(v), bcast(wy), mul2(v, bcast(wx)));
 }
 
 template <int DIR>
-__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
-    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = rot90<DIR>(csub(a1, a3));
-    a0 = cadd(t0, t2); a1 = cadd(t1, t3); a2 = csub(t0, t2); a3 = csub(t1, t3);
+__device__ __forceinline__ void dft4(cpx& a0, cpx& a1, cpx& a2, cpx& a3) {
+    const cpx t0 = add2(a0, a2), t1 = sub2(a0, a2), t2 = add2(a1, a3), t3 = sub2(a1, a3);
+    a0 = add2(t0, t2); a2 = sub2(t0, t2);
+    a1 = add2(t1, rot90<DIR>(t3)); a3 = sub2(t1, rot90<DIR>(t3));
 }
 
 template <int DIR>
-__device__ __forceinline__ void dft8(float2 (&v)[8]) {
+__device__ __forceinline__ void dft8(cpx (&v)[8]) {
     dft4<DIR>(v[0], v[2], v[4], v[6]);        // even samples -> E[0..3] in v[0],v[2],v[4],v[6]
     dft4<DIR>(v[1], v[3], v[5], v[7]);        // odd  samples -> O[0..3] in v[1],v[3],v[5],v[7]
     const float h = 0.70710678118654752440f;
-    float2 o1 = v[3], o2 = v[5], o3 = v[7];
-    if (DIR < 0) {
-        o1 = make_float2(h * (o1.x + o1.y), h * (o1.y - o1.x));       // * (1-i)/sqrt2
-        o2 = make_float2(o2.y, -o2.x);                               // * -i
-        o3 = make_float2(h * (o3.y - o3.x), -h * (o3.x + o3.y));     // * (-1-i)/sqrt2
-    } else {
-        o1 = make_float2(h * (o1.x - o1.y), h * (o1.x + o1.y));       // * (1+i)/sqrt2
-        o2 = make_float2(-o2.y, o2.x);                               // * +i
-        o3 = make_float2(-h * (o3.x + o3.y), h * (o3.x - o3.y));     // * (-1+i)/sqrt2
-    }
-    float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
-    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
-    v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
-    v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
-    v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+    // O1 * (1 -+ i)/sqrt2 = h (O1 + rot O1),  O3 * (-1 -+ i)/sqrt2 = -h (O3 - rot O3),  O2 * (-+i) = rot O2;
+    // the factor h rides the final butterfly as an FFMA2
+    const cpx s1 = add2(v[3], rot90<DIR>(v[3])), s3 = sub2(v[7], rot90<DIR>(v[7]));
+    const cpx e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1], o2 = v[5];
+    v[0] = add2(e0, o0);                  v[4] = sub2(e0, o0);
+    v[1] = fma2(s1, bcast(h), e1);        v[5] = fma2(s1, bcast(-h), e1);
+    v[2] = add2(e2, rot90<DIR>(o2));      v[6] = sub2(e2, rot90<DIR>(o2));
+    v[3] = fma2(s3, bcast(-h), e3);       v[7] = fma2(s3, bcast(h), e3);
 }
 
 template <int R, int DIR> struct Dft;
 template <int DIR> struct Dft<4, DIR> {
-    __device__ __forceinline__ static void run(float2 (&v)[4]) { dft4<DIR>(v[0], v[1], v[2], v[3]); }
+    __device__ __forceinline__ static void run(cpx (&v)[4]) { dft4<DIR>(v[0], v[1], v[2], v[3]); }
 };
 template <int DIR> struct Dft<8, DIR> {
-    __device__ __forceinline__ static void run(float2 (&v)[8]) { dft8<DIR>(v); }
+    __device__ __forceinline__ static void run(cpx (&v)[8]) { dft8<DIR>(v); }
 };
 
 // Per-lane base offsets into the padded buffer (float2 units), computed once per warp.
@@ -116,7 +130,7 @@ struct LaneBase {
 // One Stockham stage on register data: twiddle (k = j mod Ns), R-point DFT.
 // v[b][r] holds input j + r*N/R of butterfly j = lane + 32 b.
 template <int N, int R, bool TWIDDLE, bool PER_B, int DIR>
-__device__ __forceinline__ void stage_compute(float2 (&v)[N / R / 32][R], const float4* __restrict__ tw, int lane) {
+__device__ __forceinline__ void stage_compute(cpx (&v)[N / R / 32][R], const float4* __restrict__ tw, int lane) {
     constexpr int NB = N / R / 32;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
@@ -135,7 +149,7 @@ __device__ __forceinline__ void stage_compute(float2 (&v)[N / R / 32][R], const 
 // The same with the twiddles of the stage in registers: stage 1 has k = j mod R0 = lane mod R0 for every b, so one
 // set of R-1 twiddles serves the whole tile (loaded once per warp, 32 shared-memory wavefronts per frame saved).
 template <int N, int R, int DIR>
-__device__ __forceinline__ void stage_compute_reg(float2 (&v)[N / R / 32][R], const float4 (&w)[R / 2]) {
+__device__ __forceinline__ void stage_compute_reg(cpx (&v)[N / R / 32][R], const float4 (&w)[R / 2]) {
 #pragma unroll
     for (int b = 0; b < N / R / 32; ++b) {
 #pragma unroll
@@ -147,18 +161,18 @@ __device__ __forceinline__ void stage_compute_reg(float2 (&v)[N / R / 32][R], co
     }
 }
 
-// Complex FFT of N points.  First-stage inputs come from `first` (functor (m, c) -> float2) and the
-// result of the last stage is handed to `last` (functor (m, c, float2)) in natural order; m = lane + c
+// Complex FFT of N points.  First-stage inputs come from `first` (functor (m, c) -> cpx) and the
+// result of the last stage is handed to `last` (functor (m, c, cpx)) in natural order; m = lane + c
 // with c a compile-time multiple of 32, so callers can address  base(lane) + padc(c).
 template <int NFFT, int DIR, class First, class Last>
-__device__ __forceinline__ void fft_warp(float2* buf, const float4* __restrict__ tw, const float4 (&tw1)[Plan<NFFT>::R1 / 2],
+__device__ __forceinline__ void fft_warp(cpx* buf, const float4* __restrict__ tw, const float4 (&tw1)[Plan<NFFT>::R1 / 2],
                                          int lane, const LaneBase<NFFT>& lb, First first, Last last) {
     using P = Plan<NFFT>;
     using L = TwLayout<NFFT>;
     constexpr int N = P::N;
     {   // stage 0: Ns = 1, no twiddles
         constexpr int R = P::R0, NB = N / R / 32;
-        float2 v[NB][R];
+        cpx v[NB][R];
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
@@ -173,7 +187,7 @@ __device__ __forceinline__ void fft_warp(float2* buf, const float4* __restrict__
     __syncwarp();
     {   // stage 1: Ns = R0
         constexpr int R = P::R1, NB = N / R / 32;
-        float2 v[NB][R];
+        cpx v[NB][R];
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
@@ -188,7 +202,7 @@ __device__ __forceinline__ void fft_warp(float2* buf, const float4* __restrict__
     __syncwarp();
     {   // stage 2: Ns = R0*R1 = N/R2, outputs j + r*Ns in natural order
         constexpr int R = P::R2, NB = N / R / 32;
-        float2 v[NB][R];
+        cpx v[NB][R];
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll

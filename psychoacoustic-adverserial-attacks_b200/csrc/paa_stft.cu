@@ -199,66 +199,112 @@ __device__ __forceinline__ void apply_op(const StftArgs& a, const float* tbl, fl
     else if (SCALED) { re *= c; im *= c; }
 }
 
+// ---- packed per-bin operators of the fused kernel ---------------------------------------------------
+// A real gain per bin commutes with conjugation, so the same function serves X[k] and conj(X[N-k]).
+// OP_PHON: |X'| = min(|X| + 1e-8, lim[k]) with one MUFU.RSQ (|X| = P rsqrt(P), unit phasor X rsqrt(P)); `bad` is
+// raised when P is zero / denormal / NaN, and the caller then redoes the whole frame with op_phon (exact magnitude,
+// phase from atan2 like torch.angle) -- one vote per frame instead of one per bin.
+__device__ __forceinline__ float rsqrt_ftz(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+template <int OP, bool SCALED>
+__device__ __forceinline__ cpx apply_op2(const StftArgs& a, const float* tbl, float scale, float c, int k, cpx X, bool& bad) {
+    if (OP == OP_MASK) return mul2(X, bcast((k < a.k_lo || k >= a.k_hi) ? (SCALED ? c : 1.f) : 0.f));
+    if (OP == OP_SCALE) return mul2(X, bcast(scale));               // caller pre-multiplies scale by c
+    if (OP == OP_PHON) {
+        float re, im;
+        up(X, re, im);
+        const float P = fmaf(re, re, im * im);
+        bad = bad || !(P > 1e-36f);
+        const float r = rsqrt_ftz(P);
+        const float xc = fmaf(P * r, c, 1e-8f * c);                 // c * (|X| + 1e-8)
+        return mul2(X, bcast(fminf(xc, tbl[k]) * r));               // a NaN bin stays NaN through r
+    }
+    return SCALED ? mul2(X, bcast(c)) : X;
+}
+
 // ---- the spectral middle of one frame -----------------------------------------------------------
-// Works on conjugate-symmetric pairs (k, N-k) of the half-length complex FFT held in `buf`:
-//   forward split  Z -> X[k], X[N-k]   |   op / store / reduce   |   inverse merge  X' -> Z' (scaled by 1/n_fft)
+// Works on conjugate-symmetric pairs (k, N-k) of the half-length complex FFT held in `buf` in natural, un-padded
+// order (ascending and descending runs of 32 are both bank-conflict free):
+//   forward split  Z -> X[k], conj X[N-k]   |   op / store / reduce   |   inverse merge  X' -> Z' (scaled by 1/n_fft)
 // Lane l handles k = l + 32 i; k = 0 pairs DC with Nyquist (Z[N] = Z[0]); k = N/2 pairs with itself.
-template <int NFFT, int SRC, int SINK, int OP>
-__device__ __forceinline__ void spectral_middle(const StftArgs& a, float2* buf, const float2* __restrict__ post,
-                                                const float* tbl, float scale, int lane, const LaneBase<NFFT>& lb,
-                                                long long spec_off, float& acc) {
+// Returns true when OP_PHON met a bin the fast operator cannot serve (SLOW = false only).
+template <int NFFT, int SRC, int SINK, int OP, bool SLOW>
+__device__ __forceinline__ bool spectral_middle(const StftArgs& a, cpx* buf, const float2* __restrict__ post,
+                                                const float* tbl, float scale, int lane, long long spec_off, float& acc) {
     using P = Plan<NFFT>;
     constexpr int N = P::N;
-    constexpr float kC = 2.f / (float)NFFT;      // see apply_op: folded into the operator on the way to the inverse
+    constexpr float kC = 2.f / (float)NFFT;      // folded into the operator on the way to the inverse
     constexpr bool TO_TIME = SINK == SINK_TIME;
-    // SELF: the k = N/2 bin, its own partner.
-    auto pair = [&](int k, int ia, int ib, auto self_tag, bool commit) {
-        constexpr bool SELF = decltype(self_tag)::value;
+    bool bad = false;
+    // SELF: the k = N/2 bin, its own partner.  FIRST: the iteration that holds k = 0 (lane 0).
+    auto pair = [&](int k, int ia, int ib, auto self_tag, auto first_tag, bool commit) {
+        constexpr bool SELF = decltype(self_tag)::value, FIRST = decltype(first_tag)::value;
         const int kn = N - k;                       // partner bin; for k == 0 this is the Nyquist bin N
-        float2 X, Y;                                // X = X[k], Y = X[N-k]
+        cpx X, Yc;                                  // X = X[k], Yc = conj(X[N-k])
+        float2 w = make_float2(0.f, 0.f);
+        if (SRC == SRC_TIME || TO_TIME) w = post[k];               // (cos, sin) of 2 pi k / n_fft
         if (SRC == SRC_TIME) {
-            const float2 za = buf[ia], zb = SELF ? za : buf[ib];
-            const float2 w = post[k];               // (cos, sin) of 2 pi k / n_fft
-            // the forward window table holds w/2, so Z is already halved: E = za + conj(zb), O = (za - conj(zb)) / i
-            const float er = za.x + zb.x, ei = za.y - zb.y;
-            const float o_r = za.y + zb.y, o_i = zb.x - za.x;
-            const float tr = w.x * o_r + w.y * o_i, ti = w.x * o_i - w.y * o_r;
-            X = make_float2(er + tr, ei + ti);
-            Y = make_float2(er - tr, -(ei - ti));
+            const cpx za = buf[ia], zb = SELF ? za : buf[ib];
+            // the forward window table holds w/2, so Z is already halved:
+            //   E = za + conj(zb),  D = za - conj(zb),  O = -i D,  T = O conj(w) = (-i D) wx + (-D) wy
+            const cpx E = add2(za, conj2(zb)), D = sub2(za, conj2(zb));
+            const cpx T = fma2(neg2(D), bcast(w.y), mul2(rot90<-1>(D), bcast(w.x)));
+            X = add2(E, T);
+            Yc = sub2(E, T);
         } else {
-            X = a.spec_in[spec_off + (long long)k * a.sf];
-            Y = SELF ? X : a.spec_in[spec_off + (long long)kn * a.sf];
+            const float2 x = a.spec_in[spec_off + (long long)k * a.sf];
+            const float2 y = SELF ? x : a.spec_in[spec_off + (long long)kn * a.sf];
+            X = pk(x.x, x.y);
+            Yc = pk(y.x, -y.y);
         }
         if (SINK == SINK_REDUCE) {
-            const float t0 = fm_term<true>(a, tbl, N + 1, k, X.x, X.y);
+            const float t0 = fm_term<true>(a, tbl, N + 1, k, cre(X), cim(X));
             if (commit) acc += t0;
-            if (!SELF) acc += fm_term<true>(a, tbl, N + 1, kn, Y.x, Y.y);
+            if (!SELF) acc += fm_term<true>(a, tbl, N + 1, kn, cre(Yc), -cim(Yc));
             return;
         }
-        apply_op<OP, TO_TIME>(a, tbl, scale, kC, k, X.x, X.y);
-        if (!SELF) apply_op<OP, TO_TIME>(a, tbl, scale, kC, kn, Y.x, Y.y);
-        else Y = X;
+        if (SLOW && OP == OP_PHON) {
+            float xr, xi, yr, yi;
+            up(X, xr, xi);
+            up(Yc, yr, yi);
+            yi = -yi;
+            op_phon(tbl, k, TO_TIME ? kC : 1.f, xr, xi);
+            if (!SELF) op_phon(tbl, kn, TO_TIME ? kC : 1.f, yr, yi);
+            X = pk(xr, xi);
+            Yc = SELF ? conj2(X) : pk(yr, -yi);
+        } else {
+            X = apply_op2<OP, TO_TIME>(a, tbl, scale, kC, k, X, bad);
+            if (!SELF) Yc = apply_op2<OP, TO_TIME>(a, tbl, scale, kC, kn, Yc, bad);
+            else Yc = conj2(X);
+        }
         if (SINK == SINK_SPEC) {
-            if (commit) a.spec_out[spec_off + (long long)k * a.sf] = X;
-            if (!SELF) a.spec_out[spec_off + (long long)kn * a.sf] = Y;
+            if (commit) a.spec_out[spec_off + (long long)k * a.sf] = make_float2(cre(X), cim(X));
+            if (!SELF) a.spec_out[spec_off + (long long)kn * a.sf] = make_float2(cre(Yc), -cim(Yc));
             return;
         }
         // inverse merge; irfft ignores the imaginary parts of the DC and Nyquist bins
-        if (k == 0) { X.y = 0.f; Y.y = 0.f; }
-        const float2 w = post[k];
-        const float ar = X.x + Y.x, ai = X.y - Y.y, br = X.x - Y.x, bi = X.y + Y.y;
-        const float pr = w.x * br - w.y * bi, pi = w.x * bi + w.y * br;
-        if (commit) buf[ia] = make_float2(ar - pi, ai + pr);
-        if (!SELF && k != 0) buf[ib] = make_float2(ar + pi, pr - ai);
+        if (FIRST && k == 0) { X = pk(cre(X), 0.f); Yc = pk(cre(Yc), 0.f); }
+        //   A = X + conj(Y),  B = X - conj(Y),  p = w B,  Z'[k] = A + i p,  Z'[N-k] = conj(A) + swap(p)
+        const cpx A = add2(X, Yc), Bv = sub2(X, Yc);
+        const cpx p = fma2(rot90<+1>(Bv), bcast(w.y), mul2(Bv, bcast(w.x)));
+        if (commit) buf[ia] = add2(A, rot90<+1>(p));
+        if (!SELF && !(FIRST && k == 0)) buf[ib] = add2(conj2(A), swap2(p));
     };
-#pragma unroll 2
-    for (int i = 0; i < N / 64; ++i) {
-        const int k = lane + 32 * i;
-        const int kb = (N - k) & (N - 1);           // storage index of the partner (Z[N] aliases Z[0])
-        pair(k, lb.ld + padc(32 * i), padc(kb), std::false_type{}, true);
+    // partner index N - k = (32 - lane) + (N - 32 (i + 1)): one per-lane base + a compile-time offset; only k = 0
+    // (lane 0 of the first iteration) wraps to Z[0]
+    const int pb = 32 - lane;
+    if (SLOW) {                                 // rare path: keep it small (rolled, run-time indices)
+#pragma unroll 1
+        for (int k = lane; k < N / 2; k += 32) pair(k, k, (N - k) & (N - 1), std::false_type{}, std::true_type{}, true);
+    } else {
+        pair(lane, lane, lane == 0 ? 0 : pb + (N - 32), std::false_type{}, std::true_type{}, true);
+#pragma unroll
+        for (int i = 1; i < N / 64; ++i)
+            pair(lane + 32 * i, lane + 32 * i, pb + (N - 32 * (i + 1)), std::false_type{}, std::false_type{}, true);
     }
-    // the self-paired bin: every lane computes it (the per-bin operators use warp votes), lane 0 commits
-    pair(N / 2, padc(N / 2), padc(N / 2), std::true_type{}, lane == 0);
+    // the self-paired bin: every lane computes it, lane 0 commits
+    pair(N / 2, N / 2, N / 2, std::true_type{}, std::false_type{}, lane == 0);
+    return bad;
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
@@ -393,10 +439,10 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     mbar_wait(&bar, 0);
     // this lane's slice of the (halved) window lives in registers for the whole tile: the first forward stage and the
     // last inverse stage touch the same points m = lane + 32*j, j = 0 .. N/32-1 (saves 64 smem wavefronts per frame)
-    float2 wreg[N / 32];
+    cpx wreg[N / 32];
     {
         const float* s_win = reinterpret_cast<const float*>(s_fft);      // visiting copy, overwritten by the first FFT
-        const float2* win2 = reinterpret_cast<const float2*>(s_win);
+        const cpx* win2 = reinterpret_cast<const cpx*>(s_win);
 #pragma unroll
         for (int j = 0; j < N / 32; ++j) wreg[j] = win2[lane + 32 * j];
         if (SINK == SINK_TIME) {
@@ -410,44 +456,55 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     __syncthreads();
 
     // ---- frames ----------------------------------------------------------------------------------
-    float2* buf = s_fft + (size_t)warp * BufLayout<NFFT>::kFloat2;
+    cpx* buf = reinterpret_cast<cpx*>(s_fft) + (size_t)warp * BufLayout<NFFT>::kFloat2;
     const LaneBase<NFFT> lb(lane);
     float4 tw1[P::R1 / 2];                     // stage-1 twiddles of this lane (same for every butterfly and frame)
 #pragma unroll
     for (int q = 0; q < P::R1 / 2; ++q) tw1[q] = s_tw[q * 32 + lane];
     float acc = 0.f;
+    const int olim = S * hop;
     for (int r = 0; r < R; ++r) {
         for (int q = 0; q < a.Q; ++q) {
             const int f = (warp * a.Q + q) * R + r;
             const int t = t0 + f;
             if (t < 0 || t >= a.n_frames) continue;              // warp-uniform
             const long long spec_off = (long long)row * a.sb + (long long)t * a.st;
-            if (SRC == SRC_TIME) {
-                const float2* x2 = reinterpret_cast<const float2*>(s_in + f * hop);
-                fft_warp<NFFT, -1>(
-                    buf, s_tw, tw1, lane, lb,
-                    [&](int m, int c) { const float2 xv = x2[m], wv = wreg[c / 32]; return make_float2(xv.x * wv.x, xv.y * wv.y); },
-                    [&](int, int c, float2 v) { buf[lb.ld + padc(c)] = v; });
+            // The spectrum sits in `buf` in natural un-padded order between the transforms (m = lane + c).
+            bool slow = false;
+            for (;;) {
+                if (SRC == SRC_TIME) {
+                    const cpx* x2 = reinterpret_cast<const cpx*>(s_in + f * hop) + lane;
+                    fft_warp<NFFT, -1>(
+                        buf, s_tw, tw1, lane, lb, [&](int, int c) { return mul2(x2[c], wreg[c / 32]); },
+                        [&](int, int c, cpx v) { buf[lane + c] = v; });
+                    __syncwarp();
+                }
+                bool bad;
+                if (OP == OP_PHON && slow)
+                    bad = spectral_middle<NFFT, SRC, SINK, OP, true>(a, buf, s_post, s_thr, scale, lane, spec_off, acc);
+                else
+                    bad = spectral_middle<NFFT, SRC, SINK, OP, false>(a, buf, s_post, s_thr, scale, lane, spec_off, acc);
+                // a zero / denormal / NaN bin somewhere in the frame (rare): redo the frame with the exact operator
+                if (OP != OP_PHON || SINK == SINK_REDUCE || slow || !__any_sync(0xffffffffu, bad)) break;
+                slow = true;
                 __syncwarp();
             }
-            spectral_middle<NFFT, SRC, SINK, OP>(a, buf, s_post, s_thr, scale, lane, lb, spec_off, acc);
             if (SINK == SINK_TIME) {
                 __syncwarp();
                 const int obase = (f - R + 1) * hop;                 // owned-region coordinate of frame sample 0
-                const int olim = S * hop;
-                fft_warp<NFFT, +1>(
-                    buf, s_tw, tw1, lane, lb, [&](int, int c) { return buf[lb.ld + padc(c)]; },
-                    [&](int m, int c, float2 v) {
-                        const int o = obase + 2 * m;
-                        if (o >= 0 && o < olim) {
-                            const float2 wv = wreg[c / 32];
-                            float2* dst = reinterpret_cast<float2*>(s_ola + o);
-                            float2 cur = *dst;
-                            cur.x += v.x * wv.x;
-                            cur.y += v.y * wv.y;
-                            *dst = cur;
-                        }
-                    });
+                cpx* ola = reinterpret_cast<cpx*>(s_ola + obase) + lane;   // only dereferenced inside [0, olim)
+                if (obase >= 0 && obase + NFFT <= olim) {            // warp-uniform: the whole frame lands in the owned region
+                    fft_warp<NFFT, +1>(
+                        buf, s_tw, tw1, lane, lb, [&](int, int c) { return buf[lane + c]; },
+                        [&](int, int c, cpx v) { ola[c] = fma2(v, wreg[c / 32], ola[c]); });
+                } else {
+                    fft_warp<NFFT, +1>(
+                        buf, s_tw, tw1, lane, lb, [&](int, int c) { return buf[lane + c]; },
+                        [&](int m, int c, cpx v) {
+                            const int o = obase + 2 * m;
+                            if (o >= 0 && o < olim) ola[c] = fma2(v, wreg[c / 32], ola[c]);
+                        });
+                }
             }
         }
         if (SINK == SINK_TIME) __syncthreads();                  // next phase overlaps these frames
