@@ -23,7 +23,9 @@ template <int NFFT> struct Plan;
 // the contiguous loads conflict free and every address = per-lane base + compile-time offset.
 template <> struct Plan<1024> {
     static constexpr int N = 512, R0 = 8, R1 = 8, R2 = 8;
-    __host__ __device__ static constexpr int padB(int i) { return i + (i >> 4) + 4 * (i >> 6); }
+    // 8 spare slots per 64: conflict free for the stage-1 stores, the contiguous stage-2 loads AND the descending
+    // runs {32, 63..49}, {48..33} (+64 r) of the paired butterflies (search: tools/bank_search.py conventions)
+    __host__ __device__ static constexpr int padB(int i) { return i + 8 * (i >> 6); }
 };
 template <> struct Plan<512> {
     static constexpr int N = 256, R0 = 4, R1 = 8, R2 = 8;
@@ -42,8 +44,17 @@ template <int NFFT> struct TwLayout {
     static constexpr int NB1 = P::N / P::R1 / 32, NB2 = P::N / P::R2 / 32;
     static constexpr int kStage1 = 4 * 32;               // float4 entries
     static constexpr int kStage2 = NB2 * 4 * 32;
-    static constexpr int kTotal = kStage1 + kStage2;
+    // n_fft 1024 only: one more [4][32] block, the last-stage twiddles of the "paired" butterfly j1(lane) below
+    static constexpr int kStage2Paired = (NFFT == 1024) ? 4 * 32 : 0;
+    static constexpr int kTotal = kStage1 + kStage2 + kStage2Paired;
 };
+
+// Paired butterfly assignment (n_fft 1024, N = 512 = 8*8*8).  The last forward stage and the first inverse stage
+// run 64 radix-8 butterflies j = 0..63 on the points j + 64 r.  Bin k = j + 64 r has its conjugate partner N - k in
+// butterfly 64 - j, so lane l takes the two butterflies  j0 = l  and  j1 = 64 - l  and every (k, N-k) pair of the
+// real-FFT split / merge lives in ONE thread's registers: the spectral middle needs no shared memory at all.
+// Lane 0 takes the two self-paired butterflies 0 and 32.
+__host__ __device__ constexpr int paired_j1(int lane) { return lane ? 64 - lane : 32; }
 
 // ---- packed complex arithmetic -------------------------------------------------------------------
 // A complex value is one 64-bit register pair (re, im).  sm_100a has packed fp32 instructions (FADD2 / FMUL2 / FFMA2,
@@ -114,9 +125,10 @@ template <int DIR> struct Dft<8, DIR> {
 //   s0 : stage-0 stores       R0*j + r,  j = lane + 32 b            -> s0 + r + padc(32*R0*b)
 //   s1 : stage-1 stores       (j/R0)*R0*R1 + j%R0 + r*R0            -> s1 + padB(r*R0) + padB(32*R1*b)   (second layout)
 //   ldB: stage-2 loads        lane + c                              -> ldB + padB(c)
+//   ldB1, s01: the same for the paired butterfly j1 (b = 1 of the paired stages)
 template <int NFFT>
 struct LaneBase {
-    int ld, ldB, s0, s1;
+    int ld, ldB, s0, s1, ldB1, s01;
     __device__ __forceinline__ explicit LaneBase(int lane) {
         using P = Plan<NFFT>;
         ld = padc(lane);
@@ -124,6 +136,8 @@ struct LaneBase {
         s0 = padc(P::R0 * lane);
         const int i1 = (lane / P::R0) * P::R0 * P::R1 + (lane % P::R0);
         s1 = P::padB(i1);
+        ldB1 = P::padB(paired_j1(lane));
+        s01 = padc(P::R0 * paired_j1(lane));
     }
 };
 
@@ -161,59 +175,124 @@ __device__ __forceinline__ void stage_compute_reg(cpx (&v)[N / R / 32][R], const
     }
 }
 
+// ---- the three Stockham stages as separate pieces ---------------------------------------------------------------
+// stage 0 (Ns = 1, no twiddles): v[b][r] = input j + r*N/R0 of butterfly j; outputs go to buf at R0*j + r (first layout)
+template <int NFFT, int DIR, bool PAIRED>
+__device__ __forceinline__ void fft_stage0(cpx* buf, cpx (&v)[Plan<NFFT>::N / Plan<NFFT>::R0 / 32][Plan<NFFT>::R0], int lane,
+                                           const LaneBase<NFFT>& lb) {
+    using P = Plan<NFFT>;
+    constexpr int N = P::N, R = P::R0, NB = N / R / 32;
+    stage_compute<N, R, false, false, DIR>(v, nullptr, lane);
+    __syncwarp();                       // buf may still be read by the previous user
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (PAIRED && b == 1) buf[lb.s01 + r] = v[b][r];
+            else buf[lb.s0 + r + padc(32 * R * b)] = v[b][r];
+        }
+    __syncwarp();
+}
+// stage 1 (Ns = R0): buf -> registers -> buf (second layout)
+template <int NFFT, int DIR>
+__device__ __forceinline__ void fft_stage1(cpx* buf, const float4 (&tw1)[Plan<NFFT>::R1 / 2], const LaneBase<NFFT>& lb) {
+    using P = Plan<NFFT>;
+    constexpr int N = P::N, R = P::R1, NB = N / R / 32;
+    cpx v[NB][R];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[b][r] = buf[lb.ld + padc(32 * b + r * (N / R))];
+    stage_compute_reg<N, R, DIR>(v, tw1);
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int r = 0; r < R; ++r) buf[lb.s1 + P::padB(r * P::R0) + P::padB(32 * R * b)] = v[b][r];
+    __syncwarp();
+}
+// stage 2 (Ns = R0*R1 = N/R2): buf -> registers; v[b][r] = output j + r*Ns of butterfly j (natural order).
+// PAIRED: b = 1 is butterfly j1(lane) with its own twiddle block (table index 2).
+template <int NFFT, int DIR, bool PAIRED>
+__device__ __forceinline__ void fft_stage2(const cpx* buf, const float4* __restrict__ tw, cpx (&v)[Plan<NFFT>::N / Plan<NFFT>::R2 / 32][Plan<NFFT>::R2],
+                                           int lane, const LaneBase<NFFT>& lb) {
+    using P = Plan<NFFT>;
+    using L = TwLayout<NFFT>;
+    constexpr int N = P::N, R = P::R2, NB = N / R / 32;
+    const float4* t2 = tw + L::kStage1;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            v[b][r] = (PAIRED && b == 1) ? buf[lb.ldB1 + P::padB(r * (N / R))] : buf[lb.ldB + P::padB(32 * b + r * (N / R))];
+#pragma unroll
+        for (int q = 0; q < R / 2; ++q) {
+            const float4 w = t2[(((PAIRED && b == 1) ? 2 : b) * 4 + q) * 32 + lane];
+            if (q > 0) v[b][2 * q] = cmul_tw<DIR>(v[b][2 * q], w.x, w.y);
+            v[b][2 * q + 1] = cmul_tw<DIR>(v[b][2 * q + 1], w.z, w.w);
+        }
+        Dft<R, DIR>::run(v[b]);
+    }
+}
+
 // Complex FFT of N points.  First-stage inputs come from `first` (functor (m, c) -> cpx) and the
 // result of the last stage is handed to `last` (functor (m, c, cpx)) in natural order; m = lane + c
-// with c a compile-time multiple of 32, so callers can address  base(lane) + padc(c).
+// with c a compile-time multiple of 32, so callers can address  base(lane) + c.
 template <int NFFT, int DIR, class First, class Last>
 __device__ __forceinline__ void fft_warp(cpx* buf, const float4* __restrict__ tw, const float4 (&tw1)[Plan<NFFT>::R1 / 2],
                                          int lane, const LaneBase<NFFT>& lb, First first, Last last) {
     using P = Plan<NFFT>;
-    using L = TwLayout<NFFT>;
     constexpr int N = P::N;
-    {   // stage 0: Ns = 1, no twiddles
+    {
         constexpr int R = P::R0, NB = N / R / 32;
         cpx v[NB][R];
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int r = 0; r < R; ++r) v[b][r] = first(lane + 32 * b + r * (N / R), 32 * b + r * (N / R));
-        stage_compute<N, R, false, false, DIR>(v, tw, lane);
-        __syncwarp();                       // buf may still be read by the previous user
-#pragma unroll
-        for (int b = 0; b < NB; ++b)
-#pragma unroll
-            for (int r = 0; r < R; ++r) buf[lb.s0 + r + padc(32 * R * b)] = v[b][r];
+        fft_stage0<NFFT, DIR, false>(buf, v, lane, lb);
     }
-    __syncwarp();
-    {   // stage 1: Ns = R0
-        constexpr int R = P::R1, NB = N / R / 32;
-        cpx v[NB][R];
-#pragma unroll
-        for (int b = 0; b < NB; ++b)
-#pragma unroll
-            for (int r = 0; r < R; ++r) v[b][r] = buf[lb.ld + padc(32 * b + r * (N / R))];
-        stage_compute_reg<N, R, DIR>(v, tw1);
-        __syncwarp();
-#pragma unroll
-        for (int b = 0; b < NB; ++b)
-#pragma unroll
-            for (int r = 0; r < R; ++r) buf[lb.s1 + P::padB(r * P::R0) + P::padB(32 * R * b)] = v[b][r];
-    }
-    __syncwarp();
-    {   // stage 2: Ns = R0*R1 = N/R2, outputs j + r*Ns in natural order
+    fft_stage1<NFFT, DIR>(buf, tw1, lb);
+    {
         constexpr int R = P::R2, NB = N / R / 32;
         cpx v[NB][R];
-#pragma unroll
-        for (int b = 0; b < NB; ++b)
-#pragma unroll
-            for (int r = 0; r < R; ++r) v[b][r] = buf[lb.ldB + P::padB(32 * b + r * (N / R))];
-        stage_compute<N, R, true, true, DIR>(v, tw + L::kStage1, lane);
-        __syncwarp();
+        fft_stage2<NFFT, DIR, false>(buf, tw, v, lane, lb);
+        __syncwarp();                   // `last` may write buf
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int r = 0; r < R; ++r) last(lane + 32 * b + r * (P::R0 * P::R1), 32 * b + r * (P::R0 * P::R1), v[b][r]);
     }
+}
+
+// n_fft 1024: forward transform that leaves the half-length spectrum in registers in the paired assignment,
+//   z[0][r] = Z[lane + 64 r],   z[1][r] = Z[j1(lane) + 64 r]
+template <class First>
+__device__ __forceinline__ void fft_forward_paired(cpx* buf, const float4* __restrict__ tw, const float4 (&tw1)[4], int lane,
+                                                   const LaneBase<1024>& lb, First first, cpx (&z)[2][8]) {
+    {
+        cpx v[2][8];
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[b][r] = first(lane + 32 * b + r * 64, 32 * b + r * 64);
+        fft_stage0<1024, -1, false>(buf, v, lane, lb);
+    }
+    fft_stage1<1024, -1>(buf, tw1, lb);
+    fft_stage2<1024, -1, true>(buf, tw, z, lane, lb);
+}
+// ... and the inverse that starts from those registers; `last` as in fft_warp (natural order, m = lane + c)
+template <class Last>
+__device__ __forceinline__ void fft_inverse_paired(cpx* buf, const float4* __restrict__ tw, const float4 (&tw1)[4], int lane,
+                                                   const LaneBase<1024>& lb, cpx (&z)[2][8], Last last) {
+    fft_stage0<1024, +1, true>(buf, z, lane, lb);
+    fft_stage1<1024, +1>(buf, tw1, lb);
+    cpx v[2][8];
+    fft_stage2<1024, +1, false>(buf, tw, v, lane, lb);
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) last(lane + 32 * b + r * 64, 32 * b + r * 64, v[b][r]);
 }
 
 }  // namespace paa

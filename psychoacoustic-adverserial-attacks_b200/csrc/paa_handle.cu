@@ -40,6 +40,16 @@ void build_tables(std::vector<float>& tw, std::vector<float>& post) {
     using P = paa::Plan<NFFT>;
     stage_twiddles(tw, P::N, P::R1, P::R0);
     stage_twiddles(tw, P::N, P::R2, P::R0 * P::R1);
+    if (NFFT == 1024) {
+        // last-stage twiddles of the paired butterfly j1(lane) (paa_fft.cuh): W_N^{j1 r}, same [q][lane] float4 layout
+        for (int q = 0; q < 4; ++q)
+            for (int lane = 0; lane < 32; ++lane)
+                for (int r = 2 * q; r < 2 * q + 2; ++r) {
+                    const double th = 2.0 * M_PI * (double)paa::paired_j1(lane) * (double)r / (double)P::N;
+                    tw.push_back((float)std::cos(th));
+                    tw.push_back((float)(-std::sin(th)));
+                }
+    }
     for (int k = 0; k <= P::N / 2; ++k) {
         const double th = 2.0 * M_PI * (double)k / (double)NFFT;
         post.push_back((float)std::cos(th));

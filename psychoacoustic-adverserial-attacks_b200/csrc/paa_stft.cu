@@ -45,6 +45,7 @@ struct StftArgs {
     int blocks_per_tile;   // S (SINK_TIME) -- owned output hop blocks
     int tiles_per_row;
     int vec_ok;            // rows are 16-byte aligned: float4 tile loads allowed
+    int pf_stride;         // CTAs resident at once (SMs x CTAs per SM): CTA i prefetches the input of CTA i + pf_stride into L2
     // time-domain sink [rows, out_len]
     float* y;
     int out_len;
@@ -128,34 +129,26 @@ __device__ __forceinline__ void op_phon_db(const float* thr, int k, float& re, f
 //   |X'| = min(|X| + 1e-8, lim[k])   -- the dB round trip is the identity on un-clipped bins up to
 // fp32 rounding (~1e-6 relative, inside the 1e-5 parity bar) and log10 is monotone, so no log/exp per bin.
 // `c` is the power-of-two factor 2/n_fft the inverse transform wants folded in; lim_c[k] = c * lim[k].
-// One MUFU.RSQ gives both |X| = P * rsqrt(P) and the unit phasor X * rsqrt(P).
+// This is the exact form (true square root; phase from atan2 like torch.angle when the magnitude is zero or
+// denormal); the hot path is apply_op2's one-MUFU form, which hands frames with such bins over to this one.
+// No warp-level primitives: it also runs under the lane-0 divergence of the register-resident middle.
 __device__ __forceinline__ void op_phon(const float* lim_c, int k, float c, float& re, float& im) {
     const float P = fmaf(re, re, im * im);
-    const float r = rsqrtf(P);
+    const float m = sqrtf(P);
+    const float xc = fmaf(m, c, 1e-8f * c);           // c * (|X| + 1e-8)
     const float l = lim_c[k];
-    if (__builtin_expect(__any_sync(0xffffffffu, !(P > 1e-36f)) != 0, 0)) {
-        // some lane has a zero / denormal-magnitude bin: exact magnitude, phase from atan2 like torch.angle
-        const float m = sqrtf(P);
-        const float xc = fmaf(m, c, 1e-8f * c);
-        const float mag = (xc > l) ? l : xc;
-        if (P > 1e-36f) {
-            const float g = mag * r;
-            re *= g;
-            im *= g;
-        } else {
-            const float ph = atan2f(im, re);
-            float sn, cs;
-            sincosf(ph, &sn, &cs);
-            re = mag * cs;
-            im = mag * sn;
-        }
-        return;
-    }
-    const float xc = fmaf(P * r, c, 1e-8f * c);       // c * (|X| + 1e-8)
     const float mag = (xc > l) ? l : xc;              // NaN falls through like torch.where(db > thr, ...)
-    const float g = mag * r;
-    re *= g;
-    im *= g;
+    if (P > 1e-36f) {
+        const float g = mag * rsqrtf(P);
+        re *= g;
+        im *= g;
+    } else {
+        const float ph = atan2f(im, re);
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        re = mag * cs;
+        im = mag * sn;
+    }
 }
 // compute_fm_weighted_norm_interp (projections.py:93-113): P * w(10 log10(P+1e-10), f_k)
 // `tab` is the fm blob (global memory for the element-wise kernel, shared memory in the fused kernel).
@@ -307,6 +300,152 @@ __device__ __forceinline__ bool spectral_middle(const StftArgs& a, cpx* buf, con
     return bad;
 }
 
+// ---- n_fft 1024: the spectral middle on registers ----------------------------------------------------------
+// cos / sin (pi j / 16) as literals: after unrolling every use below is an immediate operand.
+__host__ __device__ constexpr float cpi16(int j) {
+    switch (j & 31) {
+        case 0: return 1.f;
+        case 1: return 0.98078528040323043f;
+        case 2: return 0.92387953251128674f;
+        case 3: return 0.83146961230254524f;
+        case 4: return 0.70710678118654752f;
+        case 5: return 0.55557023301960218f;
+        case 6: return 0.38268343236508977f;
+        case 7: return 0.19509032201612825f;
+        case 8: return 0.f;
+        case 9: return -0.19509032201612825f;
+        case 10: return -0.38268343236508977f;
+        case 11: return -0.55557023301960218f;
+        case 12: return -0.70710678118654752f;
+        case 13: return -0.83146961230254524f;
+        case 14: return -0.92387953251128674f;
+        case 15: return -0.98078528040323043f;
+        case 16: return -1.f;
+        default: return -cpi16(32 - (j & 31) < 16 ? 16 - (32 - (j & 31)) : 0);   // not used (j <= 16 everywhere)
+    }
+}
+__host__ __device__ constexpr float spi16(int j) { return j <= 8 ? cpi16(8 - j) : cpi16(j - 8); }
+
+// With the paired butterfly assignment (paa_fft.cuh) lane l != 0 holds z[0][r] = Z[k], k = l + 64 r, and its
+// conjugate partner z[1][7-r] = Z[N-k]; so slot r = (z[0][r], z[1][7-r]) is a complete (k, N-k) pair and split ->
+// per-bin op -> merge run on one thread's registers, in place.  The split twiddle e^{2 pi i k / n_fft} is
+// base(l) * e^{i pi r / 8}: one per-lane register and immediates.  The only shared memory the middle touches is the
+// operator's own per-bin table.
+// Lane 0 holds the two self-paired butterflies 0 and 32 (bins 64 r and 32 + 64 r), whose pairs sit in other registers:
+//   (Z[64 r], Z[64 (8-r)]) r = 1..3,   (Z[32 + 64 i], Z[32 + 64 (7-i)]) i = 0..3,   and the single bins Z[0], Z[N/2].
+// A register permutation executed by lane 0 alone (predicated moves) puts the first kind into slots 1..3 and the
+// second into slots 4..7 (with its own twiddle base and bin offset: 32 + 64 i = 64 r - 224), and slot 0 takes the two
+// singles: za = Z[0] (DC + Nyquist), zb = Z[N/2].  So all 32 lanes run the same eight slots, no divergence.
+__device__ __forceinline__ void lane0_permute_in(cpx (&z)[2][8]) {
+    const cpx a4 = z[0][4], a5 = z[0][5], a6 = z[0][6], a7 = z[0][7];
+    const cpx b0 = z[1][0], b1 = z[1][1], b2 = z[1][2], b3 = z[1][3], b4 = z[1][4], b5 = z[1][5], b6 = z[1][6], b7 = z[1][7];
+    z[1][6] = a7; z[1][5] = a6; z[1][4] = a5;                   // slots 1..3: zb = Z[64 (8-r)]
+    z[0][4] = b0; z[0][5] = b1; z[0][6] = b2; z[0][7] = b3;     // slots 4..7: za = Z[32 + 64 (r-4)]
+    z[1][3] = b7; z[1][2] = b6; z[1][1] = b5; z[1][0] = b4;     //             zb = Z[32 + 64 (11-r)]
+    z[1][7] = a4;                                               // slot 0: zb = Z[N/2]
+}
+__device__ __forceinline__ void lane0_permute_out(cpx (&z)[2][8]) {
+    const cpx a4 = z[0][4], a5 = z[0][5], a6 = z[0][6], a7 = z[0][7];
+    const cpx b0 = z[1][0], b1 = z[1][1], b2 = z[1][2], b3 = z[1][3], b4 = z[1][4], b5 = z[1][5], b6 = z[1][6], b7 = z[1][7];
+    z[0][7] = b6; z[0][6] = b5; z[0][5] = b4;
+    z[1][0] = a4; z[1][1] = a5; z[1][2] = a6; z[1][3] = a7;
+    z[1][7] = b3; z[1][6] = b2; z[1][5] = b1; z[1][4] = b0;
+    z[0][4] = b7;
+}
+
+template <int SRC, int SINK, int OP, bool SLOW>
+__device__ __forceinline__ bool middle_paired(const StftArgs& a, cpx (&z)[2][8], cpx base, const float* tbl, float scale,
+                                              int lane, long long spec_off, float& acc) {
+    constexpr int N = 512;
+    constexpr float kC = 2.f / 1024.f;           // folded into the operator on the way to the inverse
+    constexpr bool TO_TIME = SINK == SINK_TIME;
+    const bool l0 = lane == 0;
+    bool bad = false;
+    auto op = [&](cpx X, int k, bool& flag) {     // X or conj(X): a real gain commutes with conjugation
+        if (SLOW && OP == OP_PHON) {
+            float xr, xi;
+            up(X, xr, xi);
+            op_phon(tbl, k, TO_TIME ? kC : 1.f, xr, xi);
+            return pk(xr, xi);
+        }
+        return apply_op2<OP, TO_TIME>(a, tbl, scale, kC, k, X, flag);
+    };
+    // za = Z[k], zb = Z[N-k] (both in/out); w = (cos, sin) of 2 pi k / n_fft.
+    // dc (lane 0, slot 0 only): za = Z[0] yields the DC bin and the Nyquist bin N; zb is not part of the pair.
+    auto pair = [&](cpx& za, cpx& zb, int k, cpx w, bool dc) {
+        const int kn = N - k;
+        float wx, wy;
+        up(w, wx, wy);
+        cpx X, Yc;                                  // X = X[k], Yc = conj(X[N-k])
+        if (SRC == SRC_TIME) {
+            const cpx zp = dc ? za : zb;
+            // the forward window table holds w/2, so Z is already halved:
+            //   E = za + conj(zb),  D = za - conj(zb),  O = -i D,  T = O conj(w) = (-i D) wx + (-D) wy
+            const cpx E = add2(za, conj2(zp)), D = sub2(za, conj2(zp));
+            const cpx T = fma2(neg2(D), bcast(wy), mul2(rot90<-1>(D), bcast(wx)));
+            X = add2(E, T);
+            Yc = sub2(E, T);
+        } else {
+            const float2 x = a.spec_in[spec_off + (long long)k * a.sf];
+            const float2 y = a.spec_in[spec_off + (long long)kn * a.sf];
+            X = pk(x.x, x.y);
+            Yc = pk(y.x, -y.y);
+        }
+        if (SINK == SINK_REDUCE) {
+            acc += fm_term<true>(a, tbl, N + 1, k, cre(X), cim(X));
+            acc += fm_term<true>(a, tbl, N + 1, kn, cre(Yc), -cim(Yc));
+            return;
+        }
+        X = op(X, k, bad);
+        Yc = op(Yc, kn, bad);
+        if (SINK == SINK_SPEC) {
+            a.spec_out[spec_off + (long long)k * a.sf] = make_float2(cre(X), cim(X));
+            a.spec_out[spec_off + (long long)kn * a.sf] = make_float2(cre(Yc), -cim(Yc));
+            return;
+        }
+        // inverse merge; irfft ignores the imaginary parts of the DC and Nyquist bins
+        X = pk(cre(X), dc ? 0.f : cim(X));
+        Yc = pk(cre(Yc), dc ? 0.f : cim(Yc));
+        //   A = X + conj(Y),  B = X - conj(Y),  p = w B,  Z'[k] = A + i p,  Z'[N-k] = conj(A) + swap(p)
+        const cpx A = add2(X, Yc), Bv = sub2(X, Yc);
+        const cpx p = fma2(rot90<+1>(Bv), bcast(wy), mul2(Bv, bcast(wx)));
+        za = add2(A, rot90<+1>(p));
+        zb = add2(conj2(A), swap2(p));
+    };
+    if (SRC == SRC_TIME && l0) lane0_permute_in(z);
+    // slots 4..7 of lane 0 hold bins 32 + 64 (r-4) = 64 r - 224: own bin offset and twiddle base e^{-2 pi i 224 / 1024}
+    const int kB = l0 ? -224 : lane;
+    const cpx baseB = l0 ? pk(cpi16(7), -spi16(7)) : base;
+    // slot 0: a normal pair for lanes 1..31; lane 0 runs the DC/Nyquist unit on za and the N/2 unit on zb
+    {
+        const cpx half_in = z[1][7];
+        pair(z[0][0], z[1][7], lane, base, l0);
+        // the self-paired bin k = N/2 (lane 0 commits):  X = 2 conj(z),  Z' = 2 conj(X')
+        cpx Xh;
+        if (SRC == SRC_TIME) Xh = mul2(conj2(half_in), bcast(2.f));
+        else { const float2 x = a.spec_in[spec_off + (long long)(l0 ? N / 2 : lane) * a.sf]; Xh = pk(x.x, x.y); }
+        if (SINK == SINK_REDUCE) {
+            const float t = fm_term<true>(a, tbl, N + 1, N / 2, cre(Xh), cim(Xh));
+            if (l0) acc += t;
+        } else {
+            bool bad_h = false;
+            Xh = op(Xh, N / 2, bad_h);
+            bad = bad || (l0 && bad_h);
+            if (SINK == SINK_SPEC) { if (l0) a.spec_out[spec_off + (long long)(N / 2) * a.sf] = make_float2(cre(Xh), cim(Xh)); }
+            else if (l0) z[1][7] = mul2(conj2(Xh), bcast(2.f));
+        }
+    }
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+        // w = base * e^{i pi r / 8}
+        const cpx bs = r < 4 ? base : baseB;
+        const cpx w = fma2(rot90<+1>(bs), bcast(spi16(2 * r)), mul2(bs, bcast(cpi16(2 * r))));
+        pair(z[0][r], z[1][7 - r], (r < 4 ? lane : kB) + 64 * r, w, false);
+    }
+    if (SINK == SINK_TIME && l0) lane0_permute_out(z);
+    return bad;
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------
 template <int NFFT, int SRC, int SINK, int OP>
 __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(StftArgs a) {
@@ -326,8 +465,10 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     // shared-memory carve-up (all offsets multiples of 16 bytes)
     unsigned char* sp = smem;
     const float4* s_tw = (const float4*)(sp + a.off_tw);
-    const float2* s_post = (const float2*)(sp + a.off_post);
-    sp += a.off_win;                           // the window itself only visits shared memory (see below)
+    const float2* s_post = (const float2*)(sp + a.off_post);    // n_fft 512 only
+    // n_fft 1024 derives the split twiddles in registers (middle_paired): only the FFT twiddles stay resident
+    const unsigned tbl_bytes = (NFFT == 1024) ? a.off_post : a.off_win;
+    sp += tbl_bytes;                           // the window itself only visits shared memory (see below)
     float* s_thr = (float*)sp;                 // per-bin table of the operator: phon limits, or the fletcher_munson blob
     if (OP == OP_PHON || OP == OP_PHON_DB) sp += ((F * 4 + 15) / 16) * 16;
     if (SINK == SINK_REDUCE) sp += a.fm_blob_bytes;
@@ -349,8 +490,8 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     if (tid == 0) {
         // tables stay; the window lands in the (still idle) FFT buffers: every lane copies its 16 values to
         // registers and the envelope table is derived from it before the first frame overwrites it
-        mbar_expect_tx(&bar, a.blob_bytes + (SINK == SINK_REDUCE ? a.fm_blob_bytes : 0u));
-        tma_bulk_g2s(smem, a.blob, a.off_win, &bar);
+        mbar_expect_tx(&bar, tbl_bytes + (a.blob_bytes - a.off_win) + (SINK == SINK_REDUCE ? a.fm_blob_bytes : 0u));
+        tma_bulk_g2s(smem, a.blob, tbl_bytes, &bar);
         tma_bulk_g2s(s_fft, (const unsigned char*)a.blob + a.off_win, a.blob_bytes - a.off_win, &bar);
         if (SINK == SINK_REDUCE) tma_bulk_g2s(s_thr, a.fm_blob, a.fm_blob_bytes, &bar);
     }
@@ -364,7 +505,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
         const int T = a.T;
         // All global loads of a chunk are issued before any of them is consumed (kStageUnroll x 2 float4 in flight
         // per thread): the staging latency is otherwise exposed once per loop trip.
-        constexpr int kStageUnroll = 5;
+        constexpr int kStageUnroll = (NFFT == 1024) ? 9 : 5;      // 1024/256: 2240 float4 per tile = 8.75 per thread -> one trip
         const int lin4 = lin / 4;
         for (int base4 = 0; base4 < lin4; base4 += kStageUnroll * kThreadsStft) {
             float4 pv[kStageUnroll], gv[kStageUnroll];
@@ -416,6 +557,22 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     }
     if (SINK == SINK_TIME)
         for (int i4 = tid; i4 < S * hop / 4; i4 += kThreadsStft) *reinterpret_cast<float4*>(s_ola + i4 * 4) = make_float4(0, 0, 0, 0);
+    // The tile this slot's next CTA will stage: pull it from HBM into L2 now, so that its (latency-bound) prologue
+    // finds the lines there.  Reflect-padding samples at the row ends are left to the demand loads.
+    if (SRC == SRC_TIME && a.pf_stride > 0) {
+        const int nb = blockIdx.x + a.pf_stride;
+        if (nb < (int)gridDim.x) {
+            const int nrow = nb / a.tiles_per_row, nti = nb % a.tiles_per_row;
+            const int nt0 = (SINK == SINK_TIME) ? nti * S - R / 2 + 1 : nti * FT;
+            const int lo = max(nt0 * hop - NFFT / 2, 0), hi = min(nt0 * hop - NFFT / 2 + lin, a.T);
+            const float* px = a.x + (size_t)nrow * a.T;
+            const float* pg = a.grad ? a.grad + (size_t)nrow * a.T : nullptr;
+            for (int s = lo + tid * 32; s < hi; s += kThreadsStft * 32) {          // one 128-byte line per thread and trip
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(px + s));
+                if (pg) asm volatile("prefetch.global.L2 [%0];" ::"l"(pg + s));
+            }
+        }
+    }
 
     // ---- max_phon: scaled threshold  thr[k] = spl_thresh[k] - max(spl_thresh) + reference_db ------
     float scale = 1.f;
@@ -463,47 +620,66 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     for (int q = 0; q < P::R1 / 2; ++q) tw1[q] = s_tw[q * 32 + lane];
     float acc = 0.f;
     const int olim = S * hop;
+    // n_fft 1024: this lane's split-twiddle base e^{2 pi i lane / n_fft} (middle_paired), straight from the global table
+    cpx post_base = 0;
+    if (NFFT == 1024) {
+        const float2 pb = __ldg(reinterpret_cast<const float2*>((const unsigned char*)a.blob + a.off_post) + lane);
+        post_base = pk(pb.x, pb.y);
+    }
     for (int r = 0; r < R; ++r) {
         for (int q = 0; q < a.Q; ++q) {
             const int f = (warp * a.Q + q) * R + r;
             const int t = t0 + f;
             if (t < 0 || t >= a.n_frames) continue;              // warp-uniform
             const long long spec_off = (long long)row * a.sb + (long long)t * a.st;
-            // The spectrum sits in `buf` in natural un-padded order between the transforms (m = lane + c).
+            const int obase = (f - R + 1) * hop;                     // owned-region coordinate of frame sample 0
+            cpx* ola = reinterpret_cast<cpx*>(s_ola + obase) + lane;   // only dereferenced inside [0, olim)
+            const bool inside = obase >= 0 && obase + NFFT <= olim;  // warp-uniform: the whole frame lands in the owned region
+            auto ola_all = [&](int, int c, cpx v) { ola[c] = fma2(v, wreg[c / 32], ola[c]); };
+            auto ola_edge = [&](int m, int c, cpx v) {
+                const int o = obase + 2 * m;
+                if (o >= 0 && o < olim) ola[c] = fma2(v, wreg[c / 32], ola[c]);
+            };
+            const cpx* x2 = reinterpret_cast<const cpx*>(s_in + f * hop) + lane;
+            auto windowed = [&](int, int c) { return mul2(x2[c], wreg[c / 32]); };
             bool slow = false;
-            for (;;) {
-                if (SRC == SRC_TIME) {
-                    const cpx* x2 = reinterpret_cast<const cpx*>(s_in + f * hop) + lane;
-                    fft_warp<NFFT, -1>(
-                        buf, s_tw, tw1, lane, lb, [&](int, int c) { return mul2(x2[c], wreg[c / 32]); },
-                        [&](int, int c, cpx v) { buf[lane + c] = v; });
+            if constexpr (NFFT == 1024) {
+                // spectrum in registers between the transforms (paired butterflies, middle_paired)
+                cpx z[2][8];
+                for (;;) {
+                    if (SRC == SRC_TIME) fft_forward_paired(buf, s_tw, tw1, lane, lb, windowed, z);
+                    bool bad;
+                    if (OP == OP_PHON && slow) bad = middle_paired<SRC, SINK, OP, true>(a, z, post_base, s_thr, scale, lane, spec_off, acc);
+                    else bad = middle_paired<SRC, SINK, OP, false>(a, z, post_base, s_thr, scale, lane, spec_off, acc);
+                    // a zero / denormal / NaN bin somewhere in the frame (rare): redo the frame with the exact operator
+                    if (OP != OP_PHON || SINK == SINK_REDUCE || slow || !__any_sync(0xffffffffu, bad)) break;
+                    slow = true;
+                }
+                if (SINK == SINK_TIME) {
+                    if (inside) fft_inverse_paired(buf, s_tw, tw1, lane, lb, z, ola_all);
+                    else fft_inverse_paired(buf, s_tw, tw1, lane, lb, z, ola_edge);
+                }
+            } else {
+                // n_fft 512: the spectrum sits in `buf` in natural un-padded order between the transforms (m = lane + c)
+                for (;;) {
+                    if (SRC == SRC_TIME) {
+                        fft_warp<NFFT, -1>(buf, s_tw, tw1, lane, lb, windowed, [&](int, int c, cpx v) { buf[lane + c] = v; });
+                        __syncwarp();
+                    }
+                    bool bad;
+                    if (OP == OP_PHON && slow)
+                        bad = spectral_middle<NFFT, SRC, SINK, OP, true>(a, buf, s_post, s_thr, scale, lane, spec_off, acc);
+                    else
+                        bad = spectral_middle<NFFT, SRC, SINK, OP, false>(a, buf, s_post, s_thr, scale, lane, spec_off, acc);
+                    if (OP != OP_PHON || SINK == SINK_REDUCE || slow || !__any_sync(0xffffffffu, bad)) break;
+                    slow = true;
                     __syncwarp();
                 }
-                bool bad;
-                if (OP == OP_PHON && slow)
-                    bad = spectral_middle<NFFT, SRC, SINK, OP, true>(a, buf, s_post, s_thr, scale, lane, spec_off, acc);
-                else
-                    bad = spectral_middle<NFFT, SRC, SINK, OP, false>(a, buf, s_post, s_thr, scale, lane, spec_off, acc);
-                // a zero / denormal / NaN bin somewhere in the frame (rare): redo the frame with the exact operator
-                if (OP != OP_PHON || SINK == SINK_REDUCE || slow || !__any_sync(0xffffffffu, bad)) break;
-                slow = true;
-                __syncwarp();
-            }
-            if (SINK == SINK_TIME) {
-                __syncwarp();
-                const int obase = (f - R + 1) * hop;                 // owned-region coordinate of frame sample 0
-                cpx* ola = reinterpret_cast<cpx*>(s_ola + obase) + lane;   // only dereferenced inside [0, olim)
-                if (obase >= 0 && obase + NFFT <= olim) {            // warp-uniform: the whole frame lands in the owned region
-                    fft_warp<NFFT, +1>(
-                        buf, s_tw, tw1, lane, lb, [&](int, int c) { return buf[lane + c]; },
-                        [&](int, int c, cpx v) { ola[c] = fma2(v, wreg[c / 32], ola[c]); });
-                } else {
-                    fft_warp<NFFT, +1>(
-                        buf, s_tw, tw1, lane, lb, [&](int, int c) { return buf[lane + c]; },
-                        [&](int m, int c, cpx v) {
-                            const int o = obase + 2 * m;
-                            if (o >= 0 && o < olim) ola[c] = fma2(v, wreg[c / 32], ola[c]);
-                        });
+                if (SINK == SINK_TIME) {
+                    __syncwarp();
+                    auto from_buf = [&](int, int c) { return buf[lane + c]; };
+                    if (inside) fft_warp<NFFT, +1>(buf, s_tw, tw1, lane, lb, from_buf, ola_all);
+                    else fft_warp<NFFT, +1>(buf, s_tw, tw1, lane, lb, from_buf, ola_edge);
                 }
             }
         }
@@ -518,32 +694,44 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
         const float* g_win = reinterpret_cast<const float*>((const unsigned char*)a.blob + a.off_win);
         float* yr = a.y + (size_t)row * a.out_len;
         const bool vec = (a.out_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15u) == 0);
-        for (int jb = warp; jb < S; jb += kWarps) {
-            const int gb = ti * S + jb, n0 = gb * hop;
-            if (n0 >= a.out_len) break;                                   // warp-uniform
-            const int ub = gb + R / 2;                                    // newest frame covering this block
-            const bool exists = gb < a.n_frames - 1;
-            const bool interior = ub - R + 1 >= 0 && ub <= a.n_frames - 1;
-            for (int q = lane * 4; q < hop; q += 128) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (exists) {
-                    const float4 o = *reinterpret_cast<const float4*>(s_ola + jb * hop + q);
-                    float4 r;
-                    if (interior) {
-                        r = *reinterpret_cast<const float4*>(s_renv + q);
-                    } else {
-                        float e[4] = {0.f, 0.f, 0.f, 0.f};
-                        for (int d = R - 1; d >= 0; --d) {
-                            const int t = ub - d;
-                            if (t < 0 || t >= a.n_frames) continue;
+        const int hop4 = hop >> 2, n4 = S * hop4;
+        constexpr int kEpi = 4;
+        for (int e0 = tid; e0 < n4; e0 += kEpi * kThreadsStft) {
+            float4 o[kEpi], rv[kEpi];
+            int nn[kEpi];
+            bool live[kEpi];
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) { const float wv = 2.f * __ldg(g_win + d * hop + q + c); e[c] += wv * wv; }
-                        }
-                        r = make_float4(1.f / e[0], 1.f / e[1], 1.f / e[2], 1.f / e[3]);
+            for (int u = 0; u < kEpi; ++u) {
+                const int e = e0 + u * kThreadsStft;
+                const int jb = e / hop4, q = (e - jb * hop4) * 4;
+                const int gb = ti * S + jb;
+                nn[u] = gb * hop + q;
+                live[u] = e < n4 && nn[u] < a.out_len;
+                o[u] = rv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!live[u]) continue;
+                const int ub = gb + R / 2;                                    // newest frame covering this block
+                const bool exists = gb < a.n_frames - 1;
+                const bool interior = ub - R + 1 >= 0 && ub <= a.n_frames - 1;
+                if (!exists) continue;
+                o[u] = *reinterpret_cast<const float4*>(s_ola + jb * hop + q);
+                if (interior) {
+                    rv[u] = *reinterpret_cast<const float4*>(s_renv + q);
+                } else {
+                    float ev[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int d = R - 1; d >= 0; --d) {
+                        const int t = ub - d;
+                        if (t < 0 || t >= a.n_frames) continue;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { const float wv = 2.f * __ldg(g_win + d * hop + q + c); ev[c] += wv * wv; }
                     }
-                    v = make_float4(o.x * r.x, o.y * r.y, o.z * r.z, o.w * r.w);
+                    rv[u] = make_float4(1.f / ev[0], 1.f / ev[1], 1.f / ev[2], 1.f / ev[3]);
                 }
-                const int n = n0 + q;
+            }
+#pragma unroll
+            for (int u = 0; u < kEpi; ++u) {
+                if (!live[u]) continue;
+                const float4 v = make_float4(o[u].x * rv[u].x, o[u].y * rv[u].y, o[u].z * rv[u].z, o[u].w * rv[u].w);
+                const int n = nn[u];
                 if (vec && n + 3 < a.out_len) {
                     *reinterpret_cast<float4*>(yr + n) = v;
                 } else {
@@ -675,7 +863,7 @@ __global__ void k_spec_fm_partials(StftArgs a, int F) {
 template <int NFFT>
 size_t smem_bytes(const paa_handle* h, int src, int sink, int op, int FT, int S) {
     constexpr int N = NFFT / 2;
-    size_t b = h->off_window;
+    size_t b = (NFFT == 1024) ? h->off_post : h->off_window;
     if (sink == SINK_TIME) b += ((h->hop * 4 + 15) / 16) * 16;
     if (op == OP_PHON || op == OP_PHON_DB) b += (((N + 1) * 4 + 15) / 16) * 16;
     if (sink == SINK_REDUCE) b += h->fm_blob_bytes;
@@ -705,6 +893,7 @@ int launch_n(paa_handle* h, StftArgs& a, int grid, cudaStream_t st) {
 void fill_common(const paa_handle* h, StftArgs& a, int rows, int T, int n_frames) {
     a.rows = rows; a.T = T; a.n_frames = n_frames; a.hop = h->hop; a.R = h->R;
     a.Q = h->R >= 4 ? 1 : 2;
+    a.pf_stride = h->num_sms * (h->n_fft == 1024 ? 2 : 3);       // CTAs per SM as in __launch_bounds__
     a.frames_per_tile = kWarps * a.R * a.Q;
     a.blocks_per_tile = a.frames_per_tile - a.R + 1;
     a.blob = h->d_blob; a.blob_bytes = (unsigned)h->blob_bytes;
