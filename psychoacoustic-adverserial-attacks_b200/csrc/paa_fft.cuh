@@ -162,14 +162,22 @@ __device__ __forceinline__ void stage_compute(cpx (&v)[N / R / 32][R], const flo
 
 // The same with the twiddles of the stage in registers: stage 1 has k = j mod R0 = lane mod R0 for every b, so one
 // set of R-1 twiddles serves the whole tile (loaded once per warp, 32 shared-memory wavefronts per frame saved).
-template <int N, int R, int DIR>
-__device__ __forceinline__ void stage_compute_reg(cpx (&v)[N / R / 32][R], const float4 (&w)[R / 2]) {
+// W: anything indexable as w[q] -> float4 (a register array, or Tw1Shared re-reading the table per transform)
+struct Tw1Shared {
+    const float4* p;                    // &table[lane]
+    __device__ __forceinline__ float4 operator[](int q) const { return p[q * 32]; }
+};
+template <int N, int R, int DIR, class W>
+__device__ __forceinline__ void stage_compute_reg(cpx (&v)[N / R / 32][R], const W& w) {
+    float4 t[R / 2];
+#pragma unroll
+    for (int q = 0; q < R / 2; ++q) t[q] = w[q];
 #pragma unroll
     for (int b = 0; b < N / R / 32; ++b) {
 #pragma unroll
         for (int q = 0; q < R / 2; ++q) {
-            if (q > 0) v[b][2 * q] = cmul_tw<DIR>(v[b][2 * q], w[q].x, w[q].y);
-            v[b][2 * q + 1] = cmul_tw<DIR>(v[b][2 * q + 1], w[q].z, w[q].w);
+            if (q > 0) v[b][2 * q] = cmul_tw<DIR>(v[b][2 * q], t[q].x, t[q].y);
+            v[b][2 * q + 1] = cmul_tw<DIR>(v[b][2 * q + 1], t[q].z, t[q].w);
         }
         Dft<R, DIR>::run(v[b]);
     }
@@ -194,8 +202,8 @@ __device__ __forceinline__ void fft_stage0(cpx* buf, cpx (&v)[Plan<NFFT>::N / Pl
     __syncwarp();
 }
 // stage 1 (Ns = R0): buf -> registers -> buf (second layout)
-template <int NFFT, int DIR>
-__device__ __forceinline__ void fft_stage1(cpx* buf, const float4 (&tw1)[Plan<NFFT>::R1 / 2], const LaneBase<NFFT>& lb) {
+template <int NFFT, int DIR, class W>
+__device__ __forceinline__ void fft_stage1(cpx* buf, const W& tw1, const LaneBase<NFFT>& lb) {
     using P = Plan<NFFT>;
     constexpr int N = P::N, R = P::R1, NB = N / R / 32;
     cpx v[NB][R];
@@ -238,8 +246,8 @@ __device__ __forceinline__ void fft_stage2(const cpx* buf, const float4* __restr
 // Complex FFT of N points.  First-stage inputs come from `first` (functor (m, c) -> cpx) and the
 // result of the last stage is handed to `last` (functor (m, c, cpx)) in natural order; m = lane + c
 // with c a compile-time multiple of 32, so callers can address  base(lane) + c.
-template <int NFFT, int DIR, class First, class Last>
-__device__ __forceinline__ void fft_warp(cpx* buf, const float4* __restrict__ tw, const float4 (&tw1)[Plan<NFFT>::R1 / 2],
+template <int NFFT, int DIR, class W, class First, class Last>
+__device__ __forceinline__ void fft_warp(cpx* buf, const float4* __restrict__ tw, const W& tw1,
                                          int lane, const LaneBase<NFFT>& lb, First first, Last last) {
     using P = Plan<NFFT>;
     constexpr int N = P::N;
@@ -267,8 +275,8 @@ __device__ __forceinline__ void fft_warp(cpx* buf, const float4* __restrict__ tw
 
 // n_fft 1024: forward transform that leaves the half-length spectrum in registers in the paired assignment,
 //   z[0][r] = Z[lane + 64 r],   z[1][r] = Z[j1(lane) + 64 r]
-template <class First>
-__device__ __forceinline__ void fft_forward_paired(cpx* buf, const float4* __restrict__ tw, const float4 (&tw1)[4], int lane,
+template <class W, class First>
+__device__ __forceinline__ void fft_forward_paired(cpx* buf, const float4* __restrict__ tw, const W& tw1, int lane,
                                                    const LaneBase<1024>& lb, First first, cpx (&z)[2][8]) {
     {
         cpx v[2][8];
@@ -282,8 +290,8 @@ __device__ __forceinline__ void fft_forward_paired(cpx* buf, const float4* __res
     fft_stage2<1024, -1, true>(buf, tw, z, lane, lb);
 }
 // ... and the inverse that starts from those registers; `last` as in fft_warp (natural order, m = lane + c)
-template <class Last>
-__device__ __forceinline__ void fft_inverse_paired(cpx* buf, const float4* __restrict__ tw, const float4 (&tw1)[4], int lane,
+template <class W, class Last>
+__device__ __forceinline__ void fft_inverse_paired(cpx* buf, const float4* __restrict__ tw, const W& tw1, int lane,
                                                    const LaneBase<1024>& lb, cpx (&z)[2][8], Last last) {
     fft_stage0<1024, +1, true>(buf, z, lane, lb);
     fft_stage1<1024, +1>(buf, tw1, lb);

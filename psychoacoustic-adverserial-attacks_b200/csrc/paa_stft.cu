@@ -615,9 +615,13 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     // ---- frames ----------------------------------------------------------------------------------
     cpx* buf = reinterpret_cast<cpx*>(s_fft) + (size_t)warp * BufLayout<NFFT>::kFloat2;
     const LaneBase<NFFT> lb(lane);
+#ifdef PAA_TW1_SMEM
+    const Tw1Shared tw1{s_tw + lane};
+#else
     float4 tw1[P::R1 / 2];                     // stage-1 twiddles of this lane (same for every butterfly and frame)
 #pragma unroll
     for (int q = 0; q < P::R1 / 2; ++q) tw1[q] = s_tw[q * 32 + lane];
+#endif
     float acc = 0.f;
     const int olim = S * hop;
     // n_fft 1024: this lane's split-twiddle base e^{2 pi i lane / n_fft} (middle_paired), straight from the global table
@@ -695,6 +699,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
         float* yr = a.y + (size_t)row * a.out_len;
         const bool vec = (a.out_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15u) == 0);
         const int hop4 = hop >> 2, n4 = S * hop4;
+        const int hop4_shift = __ffs(hop4) - 1;                   // hop divides n_fft = 2^m, so it is a power of two
         constexpr int kEpi = 4;
         for (int e0 = tid; e0 < n4; e0 += kEpi * kThreadsStft) {
             float4 o[kEpi], rv[kEpi];
@@ -703,7 +708,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
 #pragma unroll
             for (int u = 0; u < kEpi; ++u) {
                 const int e = e0 + u * kThreadsStft;
-                const int jb = e / hop4, q = (e - jb * hop4) * 4;
+                const int jb = e >> hop4_shift, q = (e - (jb << hop4_shift)) * 4;
                 const int gb = ti * S + jb;
                 nn[u] = gb * hop + q;
                 live[u] = e < n4 && nn[u] < a.out_len;
