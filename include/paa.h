@@ -50,6 +50,23 @@ typedef struct paa_handle paa_handle;
 /* ---- optimiser step fused in front of the projection (train.py:161 / torch.optim.Adam) ---- */
 enum { PAA_STEP_NONE = 0, PAA_STEP_PGD = 1, PAA_STEP_ADAM = 2 };
 
+/* Universal-perturbation data parallelism (SURVEY.md 8e "mode U", next-row N4): G ranks attack disjoint utterance
+ * shards with ONE shared (1,T) perturbation.  The reference's step then needs the SUM over ranks of dL/dp
+ * (train.py:158 on a batch that is the union of the shards; the CTC reduction is "sum") and, for snr / tv, the clean
+ * statistics of the whole batch (projections.py:17, :58).  Instead of an all-reduce followed by the step, every rank
+ * hands the kernels the G partial buffers themselves -- peer-mapped device memory over NVLink (symmetric memory) --
+ * and the kernels add them in index order while they step: the collective is fused into the hot-path pass, every rank
+ * computes bit-identical results, and nothing but the partials crosses the links.  Making the partials visible
+ * (a device-side barrier on the caller's stream) is the caller's job. */
+#define PAA_MAX_PARTS 8
+typedef struct paa_parts {
+    int           n;                            /* ranks, 1..PAA_MAX_PARTS                                        */
+    const float*  grad[PAA_MAX_PARTS];          /* rank r's partial dL/dp [rows, T]; summed left to right in fp32  */
+    const double* clean_stats[PAA_MAX_PARTS];   /* rank r's {sum clean^2, sum |clean[t+1]-clean[t]|} (paa_clean_stats);
+                                                   NULL entries = statistics come from the `clean` argument        */
+    int64_t       clean_numel;                  /* numel of the whole clean batch (all ranks)                      */
+} paa_parts;
+
 typedef struct paa_step {
     int          mode;      /* PAA_STEP_*                                                         */
     const float* grad;      /* [rows, T] dL/dp exactly as autograd left it in p.grad               */
@@ -58,6 +75,8 @@ typedef struct paa_step {
     float*       adam_v;    /* [rows, T] exp_avg_sq, updated in place                              */
     int64_t      adam_t;    /* 1-based step count of THIS update (state['step'] after increment)   */
     double       beta1, beta2, eps;   /* torch defaults 0.9, 0.999, 1e-8 (build.py:357)            */
+    const paa_parts* parts; /* NULL, or mode U: parts->grad replaces `grad` (when non-NULL) and parts->clean_stats
+                               replaces the clean-audio reductions of snr / tv; honoured with mode NONE too */
 } paa_step;
 
 /* Layout of the float scalars every reducing projection leaves at the start of scratch. */
@@ -111,6 +130,11 @@ int paa_project_snr(paa_handle* h, const float* p_in, float* p_out, int rows, in
 int paa_project_tv(paa_handle* h, const float* p_in, float* p_out, int rows, int T,
                    const float* clean, int clean_rows, int clean_T, double tv_epsilon,
                    const paa_step* step, void* scratch, void* stream);                         /* projections.py:56-66 */
+
+/* Mode U helper: out2[0] = sum clean^2, out2[1] = sum over rows of sum_t |clean[r,t+1]-clean[r,t]| of this rank's
+ * utterances (fp64 on the device, fixed summation order); goes into paa_parts.clean_stats.  Uses the partials area of
+ * `scratch`. */
+int paa_clean_stats(paa_handle* h, const float* clean, int rows, int T, double* out2, void* scratch, void* stream);
 
 /* ---- step + projection, STFT domain (train.py:38-66): STFT -> per-bin op -> ISTFT in ONE kernel,
  * the spectrum never reaches HBM.  p_out must NOT alias p_in.  p_out is [rows, out_len]; samples

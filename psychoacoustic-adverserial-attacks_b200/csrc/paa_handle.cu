@@ -123,7 +123,8 @@ int paa_num_frames(const paa_handle* h, int T) { return (h && T >= 0) ? 1 + T / 
 size_t paa_scratch_bytes(const paa_handle* h, int rows, int T) {
     if (!h || rows < 0 || T < 0) return 0;
     // scalars + block partials always; the [rows, T] staging buffer only for the STFT-domain projections
-    return (size_t)kScalarBytes + kPartialBytes + (size_t)rows * (size_t)T * sizeof(float) + 256;
+    // (twice: mode U keeps the summed gradient of an STFT-domain projection behind the staging buffer)
+    return (size_t)kScalarBytes + kPartialBytes + 2 * (((size_t)rows * (size_t)T * sizeof(float) + 255) / 256 * 256) + 256;
 }
 
 int paa_scalars(const paa_handle* h, const void* scratch, float* out8, void* stream) {

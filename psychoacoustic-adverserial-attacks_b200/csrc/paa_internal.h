@@ -5,7 +5,7 @@
 #include <vector>
 #include "../../include/paa.h"
 
-#define PAA_VERSION 100
+#define PAA_VERSION 101
 
 // Host tables of one (n_fft, hop, sr) plan, mirrored on the device.
 struct paa_handle {
@@ -75,10 +75,17 @@ constexpr size_t kPartialBytes = (size_t)kMaxPartialBlocks * 2 * sizeof(double);
 static inline float* scratch_scalars(void* s) { return (float*)s; }
 static inline double* scratch_partials(void* s) { return (double*)((char*)s + kScalarBytes); }
 static inline float* scratch_stage(void* s) { return (float*)((char*)s + kScalarBytes + kPartialBytes); }
+// mode U, STFT-domain projections: the summed gradient, after the [rows, T] staging buffer (256-byte aligned)
+static inline float* scratch_gsum(void* s, int rows, int T) {
+    const size_t stage = ((size_t)rows * (size_t)T * sizeof(float) + 255) / 256 * 256;
+    return (float*)((char*)s + kScalarBytes + kPartialBytes + stage);
+}
 
 // ---- step parameters as the kernels see them -------------------------------------------------
 struct StepDev {
-    const float* grad;
+    const float* grad;     // == gpart[0] in mode U
+    const float* gpart[PAA_MAX_PARTS];   // mode U: per-rank partial gradients, summed in index order by the kernels
+    int nparts;            // 0 or 1: `grad` alone
     float* m;
     float* v;
     float lr;          // PGD
@@ -93,3 +100,5 @@ int paa_make_step(const paa_step* step, int* mode, StepDev* out);
 
 // time-domain launches (paa_time.cu)
 int paa_launch_adam_prepass(paa_handle* h, const float* p_in, float* p_out, int64_t n, const StepDev& sd, cudaStream_t st);
+// mode U: out[i] = sum over parts of gpart[k][i] (index order), for paths that cannot sum on the fly
+int paa_launch_sum_parts(paa_handle* h, const StepDev& sd, float* out, int64_t n, cudaStream_t st);

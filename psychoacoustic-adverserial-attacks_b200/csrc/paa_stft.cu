@@ -982,6 +982,14 @@ int prepare_source(paa_handle* h, const float* p_in, int rows, int T, const paa_
     int rc = paa_make_step(step, &mode, &sd);
     if (rc) return rc;
     *src = p_in; *grad = nullptr; *lr = 0.f;
+    if (mode != PAA_STEP_NONE && sd.nparts > 1) {
+        // mode U: tiles re-read halo samples, so the per-rank partial gradients are summed once into scratch
+        if (!scratch) return PAA_ERR_NULL;
+        float* gsum = scratch_gsum(scratch, rows, T);
+        rc = paa_launch_sum_parts(h, sd, gsum, (int64_t)rows * T, st);
+        if (rc) return rc;
+        sd.grad = gsum; sd.nparts = 0;
+    }
     if (mode == PAA_STEP_PGD) { *grad = sd.grad; *lr = sd.lr; }
     else if (mode == PAA_STEP_ADAM) {
         if (!scratch) return PAA_ERR_NULL;

@@ -39,12 +39,30 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 // streaming loads for data touched once (clean audio): do not let it displace p in L2
 __device__ __forceinline__ float4 ld4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 
+// The gradient: one buffer, or (mode U, paa_parts) the sum of up to PAA_MAX_PARTS per-rank partials that live in peer
+// GPUs' memory.  Plain loads reach peer-mapped addresses over NVLink; the parts are added left to right in fp32, so
+// every rank that passes the same list computes the same bits -- the all-reduce is folded into this pass.
+__device__ __forceinline__ float4 ldg4(const StepDev& s, int64_t i) {
+    float4 g = ld4(s.grad + i);
+#pragma unroll
+    for (int k = 1; k < PAA_MAX_PARTS; ++k)
+        if (k < s.nparts) { const float4 b = ld4(s.gpart[k] + i); g.x += b.x; g.y += b.y; g.z += b.z; g.w += b.w; }
+    return g;
+}
+__device__ __forceinline__ float ldg1(const StepDev& s, int64_t i) {
+    float g = s.grad[i];
+#pragma unroll
+    for (int k = 1; k < PAA_MAX_PARTS; ++k)
+        if (k < s.nparts) g += s.gpart[k][i];
+    return g;
+}
+
 // Loads 4 elements of p (and grad / Adam state), applies the step, stores the Adam state.
 template <int STEP, bool WRITE_STATE>
 __device__ __forceinline__ float4 stepped4(const float* p, int64_t i, const StepDev& s) {
     float4 x = ld4(p + i);
     if (STEP == PAA_STEP_NONE) return x;
-    float4 g = ld4(s.grad + i);
+    float4 g = ldg4(s, i);
     float4 m = make_float4(0, 0, 0, 0), v = m;
     if (STEP == PAA_STEP_ADAM) { m = ld4(s.m + i); v = ld4(s.v + i); }
     x.x = step_one<STEP>(x.x, g.x, m.x, v.x, s);
@@ -58,7 +76,7 @@ template <int STEP, bool WRITE_STATE>
 __device__ __forceinline__ float stepped1(const float* p, int64_t i, const StepDev& s) {
     float x = p[i];
     if (STEP == PAA_STEP_NONE) return x;
-    float g = s.grad[i], m = 0.f, v = 0.f;
+    float g = ldg1(s, i), m = 0.f, v = 0.f;
     if (STEP == PAA_STEP_ADAM) { m = s.m[i]; v = s.v[i]; }
     x = step_one<STEP>(x, g, m, v, s);
     if (STEP == PAA_STEP_ADAM && WRITE_STATE) { s.m[i] = m; s.v[i] = v; }
@@ -74,7 +92,7 @@ __device__ __forceinline__ Raw4 load_raw4(const float* p, int64_t i, const StepD
     r.p = ld4(p + i);
     r.g = r.m = r.v = make_float4(0.f, 0.f, 0.f, 0.f);
     r.np = r.ng = 0.f;
-    if (STEP != PAA_STEP_NONE) r.g = ld4(s.grad + i);
+    if (STEP != PAA_STEP_NONE) r.g = ldg4(s, i);
     if (STEP == PAA_STEP_ADAM) { r.m = ld4(s.m + i); r.v = ld4(s.v + i); }
     return r;
 }
@@ -259,7 +277,18 @@ struct FinalArgs {
     double snr_linear;   // 10**(snr_db/10), python double
     double n_p;          // numel(p)
     double n_clean;      // numel(clean)
+    // mode U: the clean-audio sum (snr: index 0, tv: index 1) is the sum of the per-rank statistics, index order
+    const double* cstat[PAA_MAX_PARTS];
+    int ncstat, cstat_idx;
 };
+__device__ __forceinline__ double clean_total(const FinalArgs& a, double local) {
+    if (a.ncstat == 0) return local;
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < PAA_MAX_PARTS; ++k)
+        if (k < a.ncstat) t += a.cstat[k][a.cstat_idx];
+    return t;
+}
 
 // The reference's data-dependent branch, in its fp32 arithmetic, from the two global sums.
 template <int NORM>
@@ -299,7 +328,7 @@ __global__ void __launch_bounds__(kThreads) k_finalize(FinalArgs a) {
     __syncthreads();
     if (threadIdx.x != 0) return;
     float scale, norm, aux0, aux1;
-    final_math<NORM>(tot[0], tot[1], a, scale, norm, aux0, aux1);
+    final_math<NORM>(tot[0], clean_total(a, tot[1]), a, scale, norm, aux0, aux1);
     a.scalars[PAA_S_SCALE] = scale;
     a.scalars[PAA_S_NORM] = norm;
     a.scalars[PAA_S_AUX0] = aux0;
@@ -398,7 +427,7 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
         if (act) r = load_raw4<STEP>(a.p_in, i4 * 4, s);
         if (NORM == NORM_TV && act && (lane == 31 || i4 + 1 >= n4) && i4 * 4 + 4 < a.n) {
             r.np = a.p_in[i4 * 4 + 4];
-            if (STEP != PAA_STEP_NONE) r.ng = s.grad[i4 * 4 + 4];
+            if (STEP != PAA_STEP_NONE) r.ng = ldg1(s, i4 * 4 + 4);
         }
         return r;
     };
@@ -489,7 +518,7 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     __syncthreads();
     if (threadIdx.x == 0) {
         float scale, norm, aux0, aux1;
-        final_math<NORM>(tot[0], tot[1], f, scale, norm, aux0, aux1);
+        final_math<NORM>(tot[0], clean_total(f, tot[1]), f, scale, norm, aux0, aux1);
         s_scale = scale;
         if (blockIdx.x == 0) {
             f.scalars[PAA_S_SCALE] = scale;
@@ -517,6 +546,43 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     }
     if (tid == 0 && sc != 1.f)
         for (int64_t i = n4 << 2; i < a.n; ++i) a.q_out[i] *= sc;
+}
+
+// ---- mode U helpers ------------------------------------------------------------------------------------------
+// Per-rank clean statistics: sum x^2 and sum_t |x[r,t+1] - x[r,t]| (no pair across a row end), block partials.
+__global__ void __launch_bounds__(kThreads) k_clean_stats(const float* __restrict__ x, int64_t n, int T, double* partials) {
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x, nth = (int64_t)gridDim.x * kThreads;
+    float e = 0.f, tv = 0.f;
+    int col = (int)(tid % T);
+    const int dcol = (int)(nth % T);
+    for (int64_t i = tid; i < n; i += nth) {
+        const float v = x[i];
+        e += v * v;
+        if (col != T - 1) tv += fabsf(x[i + 1] - v);
+        col += dcol;
+        if (col >= T) col -= T;
+    }
+    double wide[2] = {(double)e, (double)tv};
+    block_sum<2>(wide, partials + 2 * (int64_t)blockIdx.x);
+}
+__global__ void __launch_bounds__(kThreads) k_clean_stats_final(const double* partials, int nblocks, double* out2) {
+    double acc[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < nblocks; i += kThreads) { acc[0] += partials[2 * i]; acc[1] += partials[2 * i + 1]; }
+    __shared__ double tot[2];
+    block_sum<2>(acc, tot);
+    __syncthreads();
+    if (threadIdx.x == 0) { out2[0] = tot[0]; out2[1] = tot[1]; }
+}
+// out = sum of the gradient parts (for the STFT-domain projections, whose tiles re-read halo samples)
+__global__ void __launch_bounds__(kThreads) k_sum_parts(StepDev s, float* out, int64_t n, bool vec) {
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x, nth = (int64_t)gridDim.x * kThreads;
+    if (vec) {
+        const int64_t n4 = n >> 2;
+        for (int64_t i = tid; i < n4; i += nth) st4(out + i * 4, ldg4(s, i * 4));
+        for (int64_t i = (n4 << 2) + tid; i < n; i += nth) out[i] = ldg1(s, i);
+    } else {
+        for (int64_t i = tid; i < n; i += nth) out[i] = ldg1(s, i);
+    }
 }
 
 // ---- kernels: compose + clamp (train.py:136) and its backward -- the input side of the path ----
@@ -594,10 +660,17 @@ inline int grid_for(const paa_handle* h, int64_t n_vec) {
     return (int)std::max<int64_t>(1, std::min(want, cap));
 }
 
+// every gradient buffer (the one, or all parts) 16-byte aligned
+inline bool grads_aligned(const StepDev& sd) {
+    if (!aligned16(sd.grad)) return false;
+    for (int k = 1; k < sd.nparts; ++k) if (!aligned16(sd.gpart[k])) return false;
+    return true;
+}
+
 template <int STEP>
 int launch_step_clamp(paa_handle* h, const float* p_in, float* p_out, int64_t n, float lo, float hi, bool clamp,
                       const StepDev& sd, cudaStream_t st) {
-    bool vec = aligned16(p_in) && aligned16(p_out) && (STEP == PAA_STEP_NONE || aligned16(sd.grad)) &&
+    bool vec = aligned16(p_in) && aligned16(p_out) && (STEP == PAA_STEP_NONE || grads_aligned(sd)) &&
                (STEP != PAA_STEP_ADAM || (aligned16(sd.m) && aligned16(sd.v)));
     int grid = grid_for(h, vec ? (n + 3) / 4 : n);
     if (vec) k_step_clamp<STEP, true><<<grid, kThreads, 0, st>>>(p_in, p_out, n, lo, hi, clamp, sd);
@@ -620,7 +693,15 @@ int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int
                    cudaStream_t st) {
     if (!h || !p_in || !p_out || !scratch) return PAA_ERR_NULL;
     if (rows <= 0 || T <= 0) return PAA_ERR_SHAPE;
-    if (NORM != NORM_L2 && !clean) return PAA_ERR_NEED_CLEAN;
+    // mode U: the clean statistics come from the per-rank parts, the clean audio itself is not read
+    const paa_parts* parts = step ? step->parts : nullptr;
+    const bool stats = NORM != NORM_L2 && parts && parts->n > 0 && parts->clean_stats[0];
+    if (stats) {
+        if (parts->n > PAA_MAX_PARTS || parts->clean_numel <= 0) return PAA_ERR_SHAPE;
+        for (int k = 0; k < parts->n; ++k) if (!parts->clean_stats[k]) return PAA_ERR_NULL;
+        clean = nullptr; clean_n = parts->clean_numel; clean_T = 1;
+    }
+    if (NORM != NORM_L2 && !clean && !stats) return PAA_ERR_NEED_CLEAN;
     if (NORM != NORM_L2 && (clean_n <= 0 || clean_T <= 0)) return PAA_ERR_SHAPE;
     int mode = 0;
     StepDev sd{};
@@ -639,17 +720,21 @@ int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int
     }
     ReduceArgs a{};
     a.p_in = src; a.q_out = p_out; a.n = n; a.T = T;
-    a.clean = clean; a.clean_n = NORM == NORM_L2 ? 0 : clean_n; a.clean_T = clean_T > 0 ? clean_T : 1;
+    a.clean = clean; a.clean_n = (NORM == NORM_L2 || stats) ? 0 : clean_n; a.clean_T = clean_T > 0 ? clean_T : 1;
     a.partials = scratch_partials(scratch);
     a.write_q = (mode != PAA_STEP_NONE) || (src != p_out);
-    bool vec = aligned16(src) && aligned16(p_out) && (NORM == NORM_L2 || aligned16(clean)) &&
-               (NORM != NORM_TV || (T >= 4 && clean_T >= 4)) &&
-               (mode == PAA_STEP_NONE || aligned16(sd.grad)) &&
+    bool vec = aligned16(src) && aligned16(p_out) && (NORM == NORM_L2 || stats || aligned16(clean)) &&
+               (NORM != NORM_TV || (T >= 4 && (stats || clean_T >= 4))) &&
+               (mode == PAA_STEP_NONE || grads_aligned(sd)) &&
                (mode != PAA_STEP_ADAM || (aligned16(sd.m) && aligned16(sd.v)));
     int64_t work = std::max<int64_t>(n, a.clean_n);
     FinalArgs f{};
     f.partials = a.partials; f.scalars = scratch_scalars(scratch);
     f.eps = eps; f.snr_linear = snr_linear; f.n_p = (double)n; f.n_clean = (double)clean_n;
+    if (stats) {
+        f.ncstat = parts->n; f.cstat_idx = NORM == NORM_SNR ? 0 : 1;
+        for (int k = 0; k < parts->n; ++k) f.cstat[k] = parts->clean_stats[k];
+    }
     if (vec && !h->no_coop) {
         // single cooperative launch; fall through to the three-kernel form only if the device refuses it
         void* kern = nullptr;
@@ -701,8 +786,20 @@ int paa_make_step(const paa_step* step, int* mode, StepDev* out) {
     *mode = PAA_STEP_NONE;
     if (!step || step->mode == PAA_STEP_NONE) return PAA_OK;
     if (step->mode != PAA_STEP_PGD && step->mode != PAA_STEP_ADAM) return PAA_ERR_UNSUPPORTED;
-    if (!step->grad) return PAA_ERR_NULL;
-    out->grad = step->grad;
+    out->nparts = 0;
+    const paa_parts* parts = step->parts;
+    if (parts && parts->n > 0 && parts->grad[0]) {          // mode U: the gradient is the sum of the parts
+        if (parts->n > PAA_MAX_PARTS) return PAA_ERR_SHAPE;
+        for (int k = 0; k < parts->n; ++k) {
+            if (!parts->grad[k]) return PAA_ERR_NULL;
+            out->gpart[k] = parts->grad[k];
+        }
+        out->nparts = parts->n;
+        out->grad = parts->grad[0];
+    } else {
+        if (!step->grad) return PAA_ERR_NULL;
+        out->grad = step->grad;
+    }
     out->lr = (float)step->lr;
     if (step->mode == PAA_STEP_ADAM) {
         if (!step->adam_m || !step->adam_v) return PAA_ERR_NULL;
@@ -727,7 +824,29 @@ int paa_launch_adam_prepass(paa_handle* h, const float* p_in, float* p_out, int6
     return launch_step_clamp<PAA_STEP_ADAM>(h, p_in, p_out, n, 0.f, 0.f, false, sd, st);
 }
 
+int paa_launch_sum_parts(paa_handle* h, const StepDev& sd, float* out, int64_t n, cudaStream_t st) {
+    PaaDeviceGuard device_guard(h);
+    const bool vec = grads_aligned(sd) && aligned16(out);
+    k_sum_parts<<<grid_for(h, vec ? (n + 3) / 4 : n), kThreads, 0, st>>>(sd, out, n, vec);
+    PAA_LAUNCH_CHECK(h);
+    return PAA_OK;
+}
+
 extern "C" {
+
+int paa_clean_stats(paa_handle* h, const float* clean, int rows, int T, double* out2, void* scratch, void* stream) {
+    PaaDeviceGuard device_guard(h);
+    if (!h || !clean || !out2 || !scratch) return PAA_ERR_NULL;
+    if (rows <= 0 || T <= 0) return PAA_ERR_SHAPE;
+    const int64_t n = (int64_t)rows * T;
+    const int grid = std::min(grid_for(h, n), kMaxPartialBlocks);
+    cudaStream_t st = (cudaStream_t)stream;
+    k_clean_stats<<<grid, kThreads, 0, st>>>(clean, n, T, scratch_partials(scratch));
+    PAA_LAUNCH_CHECK(h);
+    k_clean_stats_final<<<1, kThreads, 0, st>>>(scratch_partials(scratch), grid, out2);
+    PAA_LAUNCH_CHECK(h);
+    return PAA_OK;
+}
 
 int paa_step_only(paa_handle* h, const float* p_in, float* p_out, int rows, int T, const paa_step* step, void* stream) {
     PaaDeviceGuard device_guard(h);

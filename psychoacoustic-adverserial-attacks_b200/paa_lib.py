@@ -28,16 +28,25 @@ EXPORTS = (
     "paa_project_linf paa_project_l2 paa_project_snr paa_project_tv paa_project_min_max_freqs "
     "paa_project_max_phon paa_project_fletcher_munson paa_step_only paa_stft paa_istft "
     "paa_spec_min_max_freqs paa_spec_phon_level paa_spec_fm_norm paa_spec_fm_project paa_compose_clamp "
-    "paa_compose_clamp_backward "
+    "paa_compose_clamp_backward paa_clean_stats "
     "paa_wer_counts"
 ).split()
+
+
+MAX_PARTS = 8
+
+
+class Parts(C.Structure):
+    """struct paa_parts -- mode U: per-rank partial gradients / clean statistics in peer-mapped device memory"""
+    _fields_ = [("n", C.c_int), ("grad", C.c_void_p * MAX_PARTS), ("clean_stats", C.c_void_p * MAX_PARTS),
+                ("clean_numel", C.c_int64)]
 
 
 class Step(C.Structure):
     """struct paa_step"""
     _fields_ = [("mode", C.c_int), ("grad", C.c_void_p), ("lr", C.c_double), ("adam_m", C.c_void_p),
                 ("adam_v", C.c_void_p), ("adam_t", C.c_int64), ("beta1", C.c_double), ("beta2", C.c_double),
-                ("eps", C.c_double)]
+                ("eps", C.c_double), ("parts", C.POINTER(Parts))]
 
 
 def _load() -> C.CDLL:
@@ -81,6 +90,7 @@ def _load() -> C.CDLL:
         "paa_spec_fm_project": (i32, [vp, vp, vp, i32, i32, i64, i64, i64, f64, vp, vp]),
         "paa_compose_clamp": (i32, [vp, vp, i32, vp, i32, i32, vp, vp]),
         "paa_compose_clamp_backward": (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp]),
+        "paa_clean_stats": (i32, [vp, vp, i32, i32, vp, vp, vp]),
         "paa_wer_counts": (i32, [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), i32, C.POINTER(i64), C.POINTER(i64)]),
     }
     for name in EXPORTS:
@@ -249,13 +259,36 @@ def stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def make_parts(grad_ptrs=None, stat_ptrs=None, clean_numel: int = 0) -> Parts:
+    """paa_parts from raw device pointers (one per rank, rank order)."""
+    n = len(grad_ptrs or stat_ptrs or ())
+    if not 0 < n <= MAX_PARTS:
+        raise ValueError(f"mode U supports 1..{MAX_PARTS} ranks, got {n}")
+    p = Parts()
+    p.n = n
+    for k in range(n):
+        p.grad[k] = int(grad_ptrs[k]) if grad_ptrs else None
+        p.clean_stats[k] = int(stat_ptrs[k]) if stat_ptrs else None
+    p.clean_numel = int(clean_numel)
+    return p
+
+
 def make_step(mode: int = STEP_NONE, grad: Optional[torch.Tensor] = None, lr: float = 0.0,
               m: Optional[torch.Tensor] = None, v: Optional[torch.Tensor] = None, t: int = 0,
-              betas=(0.9, 0.999), eps: float = 1e-8):
-    if mode == STEP_NONE:
+              betas=(0.9, 0.999), eps: float = 1e-8, parts: Optional[Parts] = None):
+    if mode == STEP_NONE and parts is None:
         return None
-    return Step(mode, grad.data_ptr(), float(lr), m.data_ptr() if m is not None else None,
-                v.data_ptr() if v is not None else None, int(t), float(betas[0]), float(betas[1]), float(eps))
+    st = Step(mode, grad.data_ptr() if grad is not None else None, float(lr), m.data_ptr() if m is not None else None,
+              v.data_ptr() if v is not None else None, int(t), float(betas[0]), float(betas[1]), float(eps),
+              C.pointer(parts) if parts is not None else None)
+    st._keep = parts                       # the pointer does not own the struct
+    return st
+
+
+def attach_parts(step: Step, parts: Optional[Parts]) -> None:
+    if parts is not None:
+        step.parts = C.pointer(parts)
+        step._keep = parts
 
 
 def step_ref(step):

@@ -90,21 +90,25 @@ def _dispatch(p, clean_audio, args, interp, spl_thresh, step):
     raise ValueError(f"Unknown norm_type: {kind!r}")
 
 
-def perturbation_constraint(p, clean_audio, args, interp, spl_thresh):
+def perturbation_constraint(p, clean_audio, args, interp, spl_thresh, parts=None):
     """Project perturbation p into the feasible set named by args.norm_type (train.py:69-99).
-    Returns a new tensor; no autograd graph is attached."""
+    Returns a new tensor; no autograd graph is attached.
+    ``parts`` (mode U, training_utils/universal.py): clean statistics of the whole multi-rank batch for snr / tv."""
     L.need_cuda(p, clean_audio)
     with torch.no_grad():
-        return _dispatch(p, clean_audio, args, interp, spl_thresh, None)
+        return _dispatch(p, clean_audio, args, interp, spl_thresh, L.make_step(L.STEP_NONE, parts=parts))
 
 
-def step_and_project(p, grad, clean_audio, args, interp, spl_thresh, optimizer: Optional[torch.optim.Optimizer] = None):
+def step_and_project(p, grad, clean_audio, args, interp, spl_thresh, optimizer: Optional[torch.optim.Optimizer] = None,
+                     parts=None):
     """One fused hot-path iteration: the optimiser step of train.py:155-175 on ``p`` given ``grad`` (= p.grad as
     autograd left it), then the projection -- in the same kernels, without host synchronisation.
 
     pgd : p + args.lr * sign(grad)                       (train.py:161)
     adam: torch.optim.Adam arithmetic on the optimiser's own state tensors (exp_avg, exp_avg_sq, step) and
           its current param_group lr, so StepLR and state_dict keep working (build.py:352-359).
+    ``parts`` (mode U, ``UniversalExchange.publish``): per-rank partial gradients / clean statistics in peer memory;
+          the kernels sum them while they step, ``grad`` is then only this rank's part.
     """
     L.need_cuda(p, grad, clean_audio)
     with torch.no_grad():
@@ -112,11 +116,12 @@ def step_and_project(p, grad, clean_audio, args, interp, spl_thresh, optimizer: 
         if g.shape != p.shape:
             raise RuntimeError(f"grad shape {tuple(g.shape)} != p shape {tuple(p.shape)}")
         if args.optimizer_type == "pgd":
-            step = L.make_step(L.STEP_PGD, g, args.lr)
+            step = L.make_step(L.STEP_PGD, g, args.lr, parts=parts)
         elif args.optimizer_type == "adam":
             if optimizer is None:
                 raise ValueError("Adam optimizer selected but optimizer is None")
             step = optimizer.fused_step_descriptor(p, g)
+            L.attach_parts(step, parts)
         else:
             raise NotImplementedError(f"Optimization type not implemented: {args.optimizer_type!r}")
         return _dispatch(p, clean_audio, args, interp, spl_thresh, step)
@@ -159,16 +164,20 @@ def train_epoch(args, train_data_loader, p, model, epoch, processor, interp, wer
                                                wer_metric=wer_metric)
             wer_scores.append(float(wer))
 
+        exchange = getattr(args, "universal_exchange", None)      # mode U: one perturbation shared by all ranks
         if args.optimizer_type == "pgd":
             (direction * loss).backward()
-            p = step_and_project(p, p.grad, clean_audio, args, interp, spl_thresh).detach()
+            parts = exchange.publish(p.grad, clean_audio) if exchange is not None else None
+            p = step_and_project(p, p.grad, clean_audio, args, interp, spl_thresh, parts=parts).detach()
         elif args.optimizer_type == "adam":
             if optimizer is None:
                 raise ValueError("Adam optimizer selected but optimizer is None")
             optimizer.zero_grad(set_to_none=True)
             (-1 * direction * loss).backward()
+            parts = exchange.publish(p.grad, clean_audio) if exchange is not None else None
             with torch.no_grad():
-                p.data = step_and_project(p.data, p.grad, clean_audio, args, interp, spl_thresh, optimizer=optimizer)
+                p.data = step_and_project(p.data, p.grad, clean_audio, args, interp, spl_thresh, optimizer=optimizer,
+                                          parts=parts)
         else:
             raise NotImplementedError(f"Optimization type not implemented: {args.optimizer_type!r}")
         times.append(time.perf_counter() - t0)

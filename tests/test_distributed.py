@@ -66,3 +66,34 @@ def test_wer_allreduce_world2():
 def test_without_process_group_is_local():
     e, w, wer = sharding.allreduce_wer(["a b"], ["a"])
     assert (e, w, wer) == (1, 2, 0.5)
+
+
+def _worker_partials(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from paa_b200.training_utils import universal
+        g = torch.full((1, 8), float(rank + 1))
+        st = torch.tensor([10.0 * (rank + 1), 0.5], dtype=torch.float64)
+        universal.reduce_partials(g, st)
+        p = torch.full((1, 4), float(rank))
+        universal.broadcast_perturbation(p, src=0)
+        out.put((rank, g.tolist(), st.tolist(), p.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_mode_u_baseline_exchange_world2():
+    """Mode U's plain exchange (all-reduce of the partial gradient and the clean statistics, broadcast of p), gloo."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_partials, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, g, st, p in got:
+        assert g == [[3.0] * 8] and st == [30.0, 1.0] and p == [[0.0] * 4]

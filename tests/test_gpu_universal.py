@@ -1,0 +1,119 @@
+"""Mode U on two GPUs: one universal (1,T) perturbation shared by two ranks that hold disjoint
+utterance shards.  The kernels read both ranks' partial gradients / clean statistics from peer memory (symmetric
+memory) and add them in rank order while they step; the result must equal the oracle's single-process step on the
+union of the shards, and must be bit-identical on both ranks.  Run with `gpurun --gpus 2`; skipped on one GPU."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+NORMS = [("linf", 1e-3), ("l2", 0.01), ("snr", 0.01), ("tv", 0.01), ("max_phon", 0.03), ("min_max_freqs", 0.01)]
+B, T, STEPS = 4, 8192, 3
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _inputs(step):
+    g = torch.Generator().manual_seed(77 + step)
+    clean = (torch.rand(B, T, generator=g) * 2 - 1) * 0.1
+    grads = torch.randn(2, 1, T, generator=g)
+    grads[:, :, ::97] = 0.0                                   # sign(0) = 0 must survive the summation
+    grads[1, :, ::97][:, ::2] = 0.0
+    return clean, grads
+
+
+def _worker(rank, world, port, backend, optimizer, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import paa_b200
+        from paa_b200.core import iso
+        from paa_b200.training_utils import build, parser, universal
+        interp = iso.build_weight_interpolator()
+        res = {}
+        for norm, sigma in NORMS:
+            args = parser.create_arg_parser().parse_args(["--norm_type", norm, "--optimizer_type", optimizer,
+                                                          "--snr_db", "40", "--lr", "1e-4"])
+            args.device = str(dev)
+            thr = build.init_phon_threshold_tensor(args)
+            p = (torch.randn(1, T, generator=torch.Generator().manual_seed(5)) * sigma).to(dev)
+            opt = None
+            if optimizer == "adam":
+                p = p.requires_grad_(True)
+                opt, _ = build.create_optimizer(args, p)
+            exch = universal.UniversalExchange(1, T, dev, backend=backend)
+            outs = []
+            for step in range(STEPS):
+                clean, grads = _inputs(step)
+                lo = rank * (B // world)
+                clean_r = clean[lo:lo + B // world].to(dev)
+                parts = exch.publish(grads[rank].to(dev), clean_r)
+                with torch.no_grad():
+                    q = paa_b200.step_and_project(p.data if opt else p, grads[rank].to(dev), clean_r, args, interp, thr,
+                                                  optimizer=opt, parts=parts)
+                    if opt:
+                        p.data = q
+                    else:
+                        p = q
+                outs.append(q.detach().cpu().clone())
+            res[norm] = outs
+        out.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(backend, optimizer):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, backend, optimizer, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return got
+
+
+def _oracle(optimizer):
+    from oracle import paa_oracle as orc
+    it = orc.build_weight_interpolator()
+    want = {}
+    for norm, sigma in NORMS:
+        hp = orc.Hyper(norm_type=norm, optimizer_type=optimizer, snr_db=40.0, lr=1e-4)
+        thr = orc.phon_threshold(hp.n_fft, hp.sr, hp.max_phon_level)
+        p = torch.randn(1, T, generator=torch.Generator().manual_seed(5)) * sigma
+        adam = orc.AdamState(m=torch.zeros(1, T), v=torch.zeros(1, T)) if optimizer == "adam" else None
+        outs = []
+        for step in range(STEPS):
+            clean, grads = _inputs(step)
+            g = grads[0] + grads[1]                             # rank order, fp32: what the kernels add
+            p = orc.step_and_constrain(p, g, clean, hp, it, thr, adam=adam)
+            outs.append(p.clone())
+        want[norm] = outs
+    return want
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="mode U needs two GPUs")
+@pytest.mark.parametrize("backend,optimizer", [("symmetric", "pgd"), ("symmetric", "adam"), ("nccl", "pgd")])
+def test_universal_two_ranks_match_single_process_oracle(backend, optimizer):
+    from conftest import rel_max
+    got = _run(backend, optimizer)
+    want = _oracle(optimizer)
+    for norm, _ in NORMS:
+        for step in range(STEPS):
+            a, b = got[0][norm][step], got[1][norm][step]
+            assert torch.equal(a, b), f"{norm} step {step}: ranks disagree"
+            err = rel_max(a, want[norm][step])
+            assert err <= 1e-5, (backend, optimizer, norm, step, err)
