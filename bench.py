@@ -130,7 +130,8 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=dev)
 
     T = SECONDS * SR
-    rows = 1 if a.universal else BATCH
+    mode_u = bool(a.mode_u) and world > 1
+    rows = 1 if (a.universal or mode_u) else BATCH
     args = pparser.create_arg_parser().parse_args(
         ["--norm_type", "snr", "--snr_db", str(SNR_DB), "--optimizer_type", "pgd", "--attack_mode", "targeted",
          "--lr", str(LR)])
@@ -144,7 +145,17 @@ def run_ours(a):
     texts = [UNTARGETED_TEXT] * BATCH
     labels = loss_helpers.encode_labels(
         loss_helpers.clean_transcripts([" ".join([args.target] * args.target_reps)] * BATCH), dev)
-    p = paa_b200.perturbation_constraint(p0.to(dev), clean_d, args, None, None)
+    exch = None
+    if mode_u:
+        # SURVEY.md 8e mode U: ONE (1,T) perturbation shared by all ranks; the kernels sum the per-rank partial
+        # gradients and clean statistics from peer memory while they step (training_utils/universal.py)
+        from paa_b200.training_utils import universal
+        exch = universal.UniversalExchange(1, T, dev, backend=a.mode_u_backend)
+        p0 = universal.broadcast_perturbation(p0.to(dev))
+        p = paa_b200.perturbation_constraint(p0, clean_d, args, None, None, parts=exch.publish(None, clean_d))
+        args.universal_exchange = exch
+    else:
+        p = paa_b200.perturbation_constraint(p0.to(dev), clean_d, args, None, None)
     direction = -1.0                      # targeted: descend the loss (train.py:124)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
 
@@ -155,7 +166,8 @@ def run_ours(a):
         (direction * out.loss).backward()
         if k is not None:
             ev[k][0].record()
-        p_new = paa_b200.step_and_project(p.detach(), p.grad, clean, args, None, None)
+        parts = exch.publish(p.grad, clean, args.norm_type) if exch is not None else None
+        p_new = paa_b200.step_and_project(p.detach(), p.grad, clean, args, None, None, parts=parts)
         if k is not None:
             ev[k][1].record()
         return p_new, out.loss.detach(), out.logits.detach().argmax(-1)
@@ -233,9 +245,12 @@ def run_ours(a):
         "warmup": a.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: targeted 'delete'x5, snr 40 dB, PGD, batch 32 x 10 s @16 kHz per GPU, "
-                               "random-init wav2vec2-base" + (", universal (1,T) perturbation" if a.universal else
-                                                             ", one perturbation row per utterance"),
-                   "batch_per_gpu": BATCH, "seconds": SECONDS, "p_rows": rows, "parallelism": f"utterance-sharded x{world}",
+                               "random-init wav2vec2-base" + (", ONE universal (1,T) perturbation shared by all ranks (mode U)"
+                                                             if mode_u else ", universal (1,T) perturbation" if a.universal
+                                                             else ", one perturbation row per utterance"),
+                   "batch_per_gpu": BATCH, "seconds": SECONDS, "p_rows": rows,
+                   "parallelism": (f"universal-dp x{world} ({a.mode_u_backend}: partial gradients summed from peer memory "
+                                   "inside the step kernel)" if mode_u else f"utterance-sharded x{world}"),
                    "l2_between_iters": "working set per step (activations, GBs) exceeds the 126 MB L2"},
         "e2e": {"value": round(e2e_value, 2), "unit": "audio-s/s", "h2d_bytes_per_step": clean_h.numel() * 4,
                 "d2h_bytes_per_step": ids_bytes + 4,
@@ -244,7 +259,7 @@ def run_ours(a):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_fused<snr,pgd>: PGD step + energy reduce + grid barrier + rescale, one cooperative launch",
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": NCU_TRAFFIC_BYTES if not a.universal else None, "algorithmic_bytes": nbytes,
+                     "traffic": NCU_TRAFFIC_BYTES if rows == BATCH else None, "algorithmic_bytes": nbytes,
                      "traffic_source": "profiles/r01f_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum of "
                                        "k_fused<1,1> (61.49 + 3.10 MB; the 20.5 MB result is still in L2 at kernel end)", "avg_call_us": round(proj_ms * 1e3, 2),
                      "peak_source": peak_src},
@@ -430,6 +445,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--universal", action="store_true", help="one (1,T) perturbation shared by the batch, as the reference's loop")
+    ap.add_argument("--mode-u", dest="mode_u", action="store_true",
+                    help="N>1: one universal perturbation shared by all ranks (SURVEY.md 8e mode U) instead of independent shards")
+    ap.add_argument("--mode-u-backend", dest="mode_u_backend", choices=["symmetric", "nccl"], default="symmetric")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", dest="no_sweep", action="store_true", help="skip the per-norm projection sweep")
     a = ap.parse_args()

@@ -167,14 +167,14 @@ def train_epoch(args, train_data_loader, p, model, epoch, processor, interp, wer
         exchange = getattr(args, "universal_exchange", None)      # mode U: one perturbation shared by all ranks
         if args.optimizer_type == "pgd":
             (direction * loss).backward()
-            parts = exchange.publish(p.grad, clean_audio) if exchange is not None else None
+            parts = exchange.publish(p.grad, clean_audio, args.norm_type) if exchange is not None else None
             p = step_and_project(p, p.grad, clean_audio, args, interp, spl_thresh, parts=parts).detach()
         elif args.optimizer_type == "adam":
             if optimizer is None:
                 raise ValueError("Adam optimizer selected but optimizer is None")
             optimizer.zero_grad(set_to_none=True)
             (-1 * direction * loss).backward()
-            parts = exchange.publish(p.grad, clean_audio) if exchange is not None else None
+            parts = exchange.publish(p.grad, clean_audio, args.norm_type) if exchange is not None else None
             with torch.no_grad():
                 p.data = step_and_project(p.data, p.grad, clean_audio, args, interp, spl_thresh, optimizer=optimizer,
                                           parts=parts)

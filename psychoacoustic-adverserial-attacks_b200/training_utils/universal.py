@@ -77,9 +77,12 @@ class UniversalExchange:
             self._numel_cache[key] = int(t.item())
         return self._numel_cache[key]
 
-    def publish(self, grad: Optional[torch.Tensor], clean: Optional[torch.Tensor]):
+    def publish(self, grad: Optional[torch.Tensor], clean: Optional[torch.Tensor], norm_type: Optional[str] = None):
         """Make this rank's partial gradient and clean statistics visible to all ranks for this step.
-        Everything is enqueued on the current stream; no host synchronisation after the first call per shape."""
+        Everything is enqueued on the current stream; no host synchronisation after the first call per shape.
+        ``norm_type``: when given, the clean statistics are computed only for the norms that use them (snr, tv)."""
+        if norm_type is not None and norm_type not in ("snr", "tv"):
+            clean = None
         slot = self.step % 2
         self.step += 1
         off = slot * self.slot

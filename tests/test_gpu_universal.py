@@ -56,7 +56,7 @@ def _worker(rank, world, port, backend, optimizer, out):
                 clean, grads = _inputs(step)
                 lo = rank * (B // world)
                 clean_r = clean[lo:lo + B // world].to(dev)
-                parts = exch.publish(grads[rank].to(dev), clean_r)
+                parts = exch.publish(grads[rank].to(dev), clean_r, norm)
                 with torch.no_grad():
                     q = paa_b200.step_and_project(p.data if opt else p, grads[rank].to(dev), clean_r, args, interp, thr,
                                                   optimizer=opt, parts=parts)
@@ -117,3 +117,63 @@ def test_universal_two_ranks_match_single_process_oracle(backend, optimizer):
             assert torch.equal(a, b), f"{norm} step {step}: ranks disagree"
             err = rel_max(a, want[norm][step])
             assert err <= 1e-5, (backend, optimizer, norm, step, err)
+
+
+# ---- the attack loop in mode U: train_epoch on two ranks against train_epoch on one rank with the union batch ----
+def _loop_worker(rank, world, port, norm, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import paa_b200  # noqa: F401
+        from paa_b200.core import loss_helpers
+        from paa_b200.training_utils import parser, train, universal
+        from test_gpu_attack_loop import tiny_model
+        args = parser.create_arg_parser().parse_args(["--norm_type", norm, "--optimizer_type", "pgd", "--snr_db", "30",
+                                                      "--lr", "1e-3", "--linf_size", "0.002"])
+        args.device = str(dev)
+        model = tiny_model(dev)
+        for q in model.parameters():
+            q.requires_grad_(False)
+        g = torch.Generator().manual_seed(3)
+        Tl, Bl = 16000, 4
+        batches = [(torch.rand(Bl, Tl, generator=g) * 2 - 1) * 0.1 for _ in range(2)]
+        texts = ["hello world this is a test"] * Bl
+        p0 = (torch.randn(1, Tl, generator=g) * 1e-3).to(dev)
+        # two ranks, half of every batch each, one shared perturbation
+        lo, hi = rank * Bl // world, (rank + 1) * Bl // world
+        args.universal_exchange = universal.UniversalExchange(1, Tl, dev)
+        res_u = train.train_epoch(args, [(b[lo:hi], texts[lo:hi]) for b in batches], p0.clone(), model, 0, None, None,
+                                  loss_helpers.WerMetric(), None, None)
+        pu = res_u.p.detach().cpu()
+        # the same epoch in one process on the whole batches (rank 0 only needs it, both run it to stay in step)
+        args.universal_exchange = None
+        res_1 = train.train_epoch(args, [(b, texts) for b in batches], p0.clone(), model, 0, None, None,
+                                  loss_helpers.WerMetric(), None, None)
+        out.put((rank, pu, res_1.p.detach().cpu()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="mode U needs two GPUs")
+@pytest.mark.parametrize("norm", ["linf", "snr"])
+def test_universal_train_epoch_reproduces_the_single_process_epoch(norm):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_loop_worker, args=(r, 2, port, norm, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {r: (pu, p1) for r, pu, p1 in (q.get(timeout=600) for _ in procs)}
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert torch.equal(got[0][0], got[1][0]), "ranks hold different perturbations"
+    pu, p1 = got[0]
+    # The shard gradients are summed in a different order than autograd sums the whole batch, so elements whose
+    # gradient is ~0 may take the other sign (a PGD step of 2*lr apart); everything else must agree.
+    differ = ((pu - p1).abs() > 1e-6 * p1.abs().max()).float().mean()
+    assert float(differ) < 5e-3, float(differ)
