@@ -16,7 +16,11 @@ CTC loss are PyTorch/cuDNN (the untouched gradient source); the step + projectio
 `roofline`: the step+projection call timed with CUDA events inside the timed steps; achieved = algorithmic bytes
             / that time; peak = MEASURED_PEAKS.json hbm_gbs.
 `cpu_baseline` / `--impl reference`: the CPU oracle port of the reference (oracle/paa_oracle.py, the one place a
-           bench leg may execute it) on a bounded sample of the same workload.
+           bench leg may execute it) on a bounded sample of the same workload.  The same leg also times the port as
+           torch eager on this GPU per norm_type (`projection_sweep.*.torch_eager_ms`, SURVEY.md 2.2's
+           kernel-for-kernel bar) and records the parity of the two results; `--no-cpu` skips all of it.
+`--mode-u` (N > 1): ONE universal perturbation shared by all ranks instead of independent shards; the kernels sum the
+           per-rank partial gradients from peer memory while they step (training_utils/universal.py).
 N > 1: one process per GPU (torchrun), each rank attacks its own utterance shard with no collective on the hot
 path; one NCCL all-reduce of the (edit errors, reference words) counters ends the run.  Weak scaling.
 """
@@ -240,6 +244,8 @@ def run_ours(a):
     achieved = nbytes / (proj_ms * 1e-3) / 1e9
     sweep = projection_sweep(dev) if (world == 1 and not a.no_sweep) else None
     cpu = cpu_baseline(a, sample_batch=2) if (world == 1 and not a.no_cpu) else None
+    if cpu and sweep:
+        baseline_torch_eager(dev, sweep)
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "audio-s/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
@@ -275,6 +281,22 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+SWEEP_CASES = [("linf", 4, 5, 1e-3, 12), ("snr", 32, 10, 0.01, 24), ("fletcher_munson", 64, 15, 0.1, 20),
+               ("fletcher_munson+identity", 64, 15, 0.1, 20), ("max_phon", 64, 15, 0.03, 12), ("tv", 128, 10, 0.01, 24),
+               ("min_max_freqs", 128, 10, 0.01, 12), ("l2", 512, 10, 0.01, 20),
+               # Adam instead of PGD: the step alone is 28 B/elem (R p,g,m,v; W p,m,v) in place of 12
+               ("linf+adam", 128, 10, 1e-3, 28), ("snr+adam", 32, 10, 0.01, 40), ("max_phon+adam", 64, 15, 0.03, 36)]
+
+
+def sweep_inputs(dev, B, sec, sigma):
+    T = sec * SR
+    g = torch.Generator(device=dev).manual_seed(1234)
+    clean = (torch.rand(B, T, generator=g, device=dev) * 2 - 1) * 0.1
+    p = torch.randn(B, T, generator=g, device=dev) * sigma
+    grad = torch.randn(B, T, generator=g, device=dev)
+    return clean, p, grad
+
+
 def projection_sweep(dev, iters: int = 20):
     """Step + projection alone at BASELINE.json's shapes, per-utterance rows, CUDA events, L2 flushed by the
     working set being larger than L2 where it is (noted per entry)."""
@@ -284,19 +306,11 @@ def projection_sweep(dev, iters: int = 20):
     peak, _ = measured_peak()
     interp = iso.build_weight_interpolator()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    cases = [("linf", 4, 5, 1e-3, 12), ("snr", 32, 10, 0.01, 24), ("fletcher_munson", 64, 15, 0.1, 20),
-             ("fletcher_munson+identity", 64, 15, 0.1, 20), ("max_phon", 64, 15, 0.03, 12), ("tv", 128, 10, 0.01, 24),
-             ("min_max_freqs", 128, 10, 0.01, 12), ("l2", 512, 10, 0.01, 20),
-             # Adam instead of PGD: the step alone is 28 B/elem (R p,g,m,v; W p,m,v) in place of 12
-             ("linf+adam", 128, 10, 1e-3, 28), ("snr+adam", 32, 10, 0.01, 40), ("max_phon+adam", 64, 15, 0.03, 36)]
     out = {}
-    for name, B, sec, sigma, bpe in cases:
+    for name, B, sec, sigma, bpe in SWEEP_CASES:
         norm = name.split("+")[0]
         T = sec * SR
-        g = torch.Generator(device=dev).manual_seed(1234)
-        clean = (torch.rand(B, T, generator=g, device=dev) * 2 - 1) * 0.1
-        p = torch.randn(B, T, generator=g, device=dev) * sigma
-        grad = torch.randn(B, T, generator=g, device=dev)
+        clean, p, grad = sweep_inputs(dev, B, sec, sigma)
         args = pparser.create_arg_parser().parse_args(["--norm_type", norm, "--optimizer_type", "pgd", "--snr_db", "40"])
         args.device = str(dev)
         # "+identity": pass B of fletcher_munson as s*q (ISTFT(s*STFT(q)) = s*q) instead of the literal round trip
@@ -322,29 +336,6 @@ def projection_sweep(dev, iters: int = 20):
         gbs = bpe * B * T / (ms * 1e-3) / 1e9
         out[name] = {"shape": f"{B}x{sec}s", "bytes_per_elem": bpe, "ms": round(ms, 4), "GB/s": round(gbs, 1),
                      "frac_of_measured_peak": round(gbs / peak, 4), "audio_s_per_s": round(B * sec / (ms * 1e-3), 1)}
-        # the kernel-for-kernel bar: the same torch ops the reference runs, eager, on this GPU
-        # (the oracle port; baseline leg only).  fletcher_munson includes its D2H -> host bilinear -> H2D trip.
-        try:
-            if opt is not None:
-                raise LookupError("no eager comparator for the Adam variants")
-            from oracle import paa_oracle as orc
-            hp = orc.Hyper(norm_type=norm, optimizer_type="pgd", snr_db=SNR_DB)
-            it_cpu = orc.build_weight_interpolator()
-            reps = 2 if norm == "fletcher_munson" else 5
-            want = orc.step_and_constrain(p, grad, clean, hp, it_cpu, thr)
-            torch.cuda.synchronize()
-            w0 = time.perf_counter()
-            for _ in range(reps):
-                orc.step_and_constrain(p, grad, clean, hp, it_cpu, thr)
-            torch.cuda.synchronize()
-            eager_ms = (time.perf_counter() - w0) * 1e3 / reps
-            got = paa_b200.step_and_project(p, grad, clean, args, interp, thr)
-            out[name]["torch_eager_ms"] = round(eager_ms, 3)
-            out[name]["speedup_vs_torch_eager"] = round(eager_ms / ms, 1)
-            out[name]["max_rel_err_vs_torch_eager"] = float(f"{float((got - want).abs().max() / want.abs().max()):.2e}")
-            del want, got
-        except Exception as exc:                                  # the comparator must never break the bench line
-            out[name]["torch_eager_ms"] = f"unavailable: {type(exc).__name__}"
         del clean, p, grad
         torch.cuda.empty_cache()
     out.update(compose_sweep(dev, flush, peak, iters))
@@ -407,6 +398,46 @@ def oracle_step_seconds(batch: int, steps: int, warmup: int, rows: int):
     for _ in range(steps):
         p, loss, _ = orc.attack_iteration(model, p, clean, [UNTARGETED_TEXT] * batch, hp)
     return (time.perf_counter() - t0) / steps
+
+
+def baseline_torch_eager(dev, sweep):
+    """Part of the baseline leg (the only place the oracle port runs): the same torch ops the reference executes,
+    eager, on THIS GPU -- the kernel-for-kernel bar of SURVEY.md 2.2 -- per norm at the sweep's shapes and seeds, written
+    next to our numbers together with the parity of the two results.  fletcher_munson includes the reference's
+    D2H -> host bilinear interpolation -> H2D round trip."""
+    import paa_b200
+    from oracle import paa_oracle as orc
+    from paa_b200.core import iso
+    from paa_b200.training_utils import build as pbuild, parser as pparser
+    interp = iso.build_weight_interpolator()
+    it_cpu = orc.build_weight_interpolator()
+    for name, B, sec, sigma, _ in SWEEP_CASES:
+        if name not in sweep or name.endswith("+adam"):
+            continue
+        norm = name.split("+")[0]
+        try:
+            clean, p, grad = sweep_inputs(dev, B, sec, sigma)
+            args = pparser.create_arg_parser().parse_args(["--norm_type", norm, "--optimizer_type", "pgd", "--snr_db", "40"])
+            args.device = str(dev)
+            args.fm_identity_roundtrip = name.endswith("+identity")
+            thr = pbuild.init_phon_threshold_tensor(args)
+            hp = orc.Hyper(norm_type=norm, optimizer_type="pgd", snr_db=SNR_DB)
+            reps = 2 if norm == "fletcher_munson" else 5
+            want = orc.step_and_constrain(p, grad, clean, hp, it_cpu, thr)
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            for _ in range(reps):
+                orc.step_and_constrain(p, grad, clean, hp, it_cpu, thr)
+            torch.cuda.synchronize()
+            eager_ms = (time.perf_counter() - w0) * 1e3 / reps
+            got = paa_b200.step_and_project(p, grad, clean, args, interp, thr)
+            sweep[name]["torch_eager_ms"] = round(eager_ms, 3)
+            sweep[name]["speedup_vs_torch_eager"] = round(eager_ms / sweep[name]["ms"], 1)
+            sweep[name]["max_rel_err_vs_torch_eager"] = float(f"{float((got - want).abs().max() / want.abs().max()):.2e}")
+            del want, got, clean, p, grad
+        except Exception as exc:                                  # the comparator must never break the bench line
+            sweep[name]["torch_eager_ms"] = f"unavailable: {type(exc).__name__}"
+        torch.cuda.empty_cache()
 
 
 def cpu_baseline(a, sample_batch: int):

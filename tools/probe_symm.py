@@ -18,8 +18,7 @@ try:
     peers = [hdl.get_buffer(r, (4096,), torch.float32) for r in range(world)]
     vals = [float(p[0]) for p in peers]
     hdl.barrier(channel=0)
-    print(f"rank {rank}: symmetric memory ok, peer values {vals}, ptrs {[hex(x) for x in hdl.buffer_ptrs]}, "
-          f"multicast {hdl.has_multicast_support('cuda', local) if hasattr(hdl, 'has_multicast_support') else '?'}", flush=True)
+    print(f"rank {rank}: symmetric memory ok, peer values {vals}, ptrs {[hex(x) for x in hdl.buffer_ptrs]}", flush=True)
 except Exception as exc:                                            # noqa: BLE001
     print(f"rank {rank}: symmetric memory FAILED: {type(exc).__name__}: {exc}", flush=True)
 dist.barrier()
