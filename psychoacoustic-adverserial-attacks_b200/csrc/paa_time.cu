@@ -21,10 +21,10 @@ enum { NORM_L2 = 0, NORM_SNR = 1, NORM_TV = 2 };
 // Adam (torch/optim/adam.py:457-547): lerp, mul+addcmul, sqrt/bias2 + eps, addcdiv.
 template <int STEP>
 __device__ __forceinline__ float step_one(float p, float g, float& m, float& v, const StepDev& s) {
-    if (STEP == PAA_STEP_PGD) {
+    if ((STEP & 3) == PAA_STEP_PGD) {
         float sg = (float)(g > 0.f) - (float)(g < 0.f);
         return p + s.lr * sg;
-    } else if (STEP == PAA_STEP_ADAM) {
+    } else if ((STEP & 3) == PAA_STEP_ADAM) {
         m = fmaf(s.w1, g - m, m);
         v = v * s.beta2;
         v = v + (s.w2 * g) * g;
@@ -42,18 +42,27 @@ __device__ __forceinline__ float4 ld4_stream(const float* p) { return __ldcs(rei
 // The gradient: one buffer, or (mode U, paa_parts) the sum of up to PAA_MAX_PARTS per-rank partials that live in peer
 // GPUs' memory.  Plain loads reach peer-mapped addresses over NVLink; the parts are added left to right in fp32, so
 // every rank that passes the same list computes the same bits -- the all-reduce is folded into this pass.
+// The multi-part form is a separate instantiation (bit 2 of the STEP template value, kStepParts) so that the
+// single-GPU kernels keep their instruction count and register budget.
+constexpr int kStepParts = 4;
+template <int STEP>
 __device__ __forceinline__ float4 ldg4(const StepDev& s, int64_t i) {
     float4 g = ld4(s.grad + i);
+    if (STEP & kStepParts) {
 #pragma unroll
-    for (int k = 1; k < PAA_MAX_PARTS; ++k)
-        if (k < s.nparts) { const float4 b = ld4(s.gpart[k] + i); g.x += b.x; g.y += b.y; g.z += b.z; g.w += b.w; }
+        for (int k = 1; k < PAA_MAX_PARTS; ++k)
+            if (k < s.nparts) { const float4 b = ld4(s.gpart[k] + i); g.x += b.x; g.y += b.y; g.z += b.z; g.w += b.w; }
+    }
     return g;
 }
+template <int STEP>
 __device__ __forceinline__ float ldg1(const StepDev& s, int64_t i) {
     float g = s.grad[i];
+    if (STEP & kStepParts) {
 #pragma unroll
-    for (int k = 1; k < PAA_MAX_PARTS; ++k)
-        if (k < s.nparts) g += s.gpart[k][i];
+        for (int k = 1; k < PAA_MAX_PARTS; ++k)
+            if (k < s.nparts) g += s.gpart[k][i];
+    }
     return g;
 }
 
@@ -61,25 +70,25 @@ __device__ __forceinline__ float ldg1(const StepDev& s, int64_t i) {
 template <int STEP, bool WRITE_STATE>
 __device__ __forceinline__ float4 stepped4(const float* p, int64_t i, const StepDev& s) {
     float4 x = ld4(p + i);
-    if (STEP == PAA_STEP_NONE) return x;
-    float4 g = ldg4(s, i);
+    if ((STEP & 3) == PAA_STEP_NONE) return x;
+    float4 g = ldg4<STEP>(s, i);
     float4 m = make_float4(0, 0, 0, 0), v = m;
-    if (STEP == PAA_STEP_ADAM) { m = ld4(s.m + i); v = ld4(s.v + i); }
-    x.x = step_one<STEP>(x.x, g.x, m.x, v.x, s);
-    x.y = step_one<STEP>(x.y, g.y, m.y, v.y, s);
-    x.z = step_one<STEP>(x.z, g.z, m.z, v.z, s);
-    x.w = step_one<STEP>(x.w, g.w, m.w, v.w, s);
-    if (STEP == PAA_STEP_ADAM && WRITE_STATE) { st4(s.m + i, m); st4(s.v + i, v); }
+    if ((STEP & 3) == PAA_STEP_ADAM) { m = ld4(s.m + i); v = ld4(s.v + i); }
+    x.x = step_one<STEP & 3>(x.x, g.x, m.x, v.x, s);
+    x.y = step_one<STEP & 3>(x.y, g.y, m.y, v.y, s);
+    x.z = step_one<STEP & 3>(x.z, g.z, m.z, v.z, s);
+    x.w = step_one<STEP & 3>(x.w, g.w, m.w, v.w, s);
+    if ((STEP & 3) == PAA_STEP_ADAM && WRITE_STATE) { st4(s.m + i, m); st4(s.v + i, v); }
     return x;
 }
 template <int STEP, bool WRITE_STATE>
 __device__ __forceinline__ float stepped1(const float* p, int64_t i, const StepDev& s) {
     float x = p[i];
-    if (STEP == PAA_STEP_NONE) return x;
-    float g = ldg1(s, i), m = 0.f, v = 0.f;
-    if (STEP == PAA_STEP_ADAM) { m = s.m[i]; v = s.v[i]; }
-    x = step_one<STEP>(x, g, m, v, s);
-    if (STEP == PAA_STEP_ADAM && WRITE_STATE) { s.m[i] = m; s.v[i] = v; }
+    if ((STEP & 3) == PAA_STEP_NONE) return x;
+    float g = ldg1<STEP>(s, i), m = 0.f, v = 0.f;
+    if ((STEP & 3) == PAA_STEP_ADAM) { m = s.m[i]; v = s.v[i]; }
+    x = step_one<STEP & 3>(x, g, m, v, s);
+    if ((STEP & 3) == PAA_STEP_ADAM && WRITE_STATE) { s.m[i] = m; s.v[i] = v; }
     return x;
 }
 
@@ -92,19 +101,19 @@ __device__ __forceinline__ Raw4 load_raw4(const float* p, int64_t i, const StepD
     r.p = ld4(p + i);
     r.g = r.m = r.v = make_float4(0.f, 0.f, 0.f, 0.f);
     r.np = r.ng = 0.f;
-    if (STEP != PAA_STEP_NONE) r.g = ldg4(s, i);
-    if (STEP == PAA_STEP_ADAM) { r.m = ld4(s.m + i); r.v = ld4(s.v + i); }
+    if ((STEP & 3) != PAA_STEP_NONE) r.g = ldg4<STEP>(s, i);
+    if ((STEP & 3) == PAA_STEP_ADAM) { r.m = ld4(s.m + i); r.v = ld4(s.v + i); }
     return r;
 }
 template <int STEP, bool WRITE_STATE>
 __device__ __forceinline__ float4 finish4(Raw4 r, int64_t i, const StepDev& s) {
-    if (STEP == PAA_STEP_NONE) return r.p;
+    if ((STEP & 3) == PAA_STEP_NONE) return r.p;
     float4 x = r.p;
-    x.x = step_one<STEP>(x.x, r.g.x, r.m.x, r.v.x, s);
-    x.y = step_one<STEP>(x.y, r.g.y, r.m.y, r.v.y, s);
-    x.z = step_one<STEP>(x.z, r.g.z, r.m.z, r.v.z, s);
-    x.w = step_one<STEP>(x.w, r.g.w, r.m.w, r.v.w, s);
-    if (STEP == PAA_STEP_ADAM && WRITE_STATE) { st4(s.m + i, r.m); st4(s.v + i, r.v); }
+    x.x = step_one<STEP & 3>(x.x, r.g.x, r.m.x, r.v.x, s);
+    x.y = step_one<STEP & 3>(x.y, r.g.y, r.m.y, r.v.y, s);
+    x.z = step_one<STEP & 3>(x.z, r.g.z, r.m.z, r.v.z, s);
+    x.w = step_one<STEP & 3>(x.w, r.g.w, r.m.w, r.v.w, s);
+    if ((STEP & 3) == PAA_STEP_ADAM && WRITE_STATE) { st4(s.m + i, r.m); st4(s.v + i, r.v); }
     return x;
 }
 
@@ -387,7 +396,7 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     const int64_t tid = (int64_t)blockIdx.x * kFT + threadIdx.x, nth = (int64_t)gridDim.x * kFT;
     const int64_t n4 = a.n >> 2;
     float acc0 = 0.f, acc1 = 0.f;
-    constexpr int RCN = (STEP == PAA_STEP_ADAM) ? 2 : kRC;      // Adam carries 4 streams: fewer register-resident float4s
+    constexpr int RCN = ((STEP & 3) == PAA_STEP_ADAM) ? 2 : kRC;      // Adam carries 4 streams: fewer register-resident float4s
     float4 keep[RCN];
 
     // total variation: row-column of each thread's current float4, advanced without 64-bit division
@@ -412,7 +421,7 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
             const bool has_next = act && (i + 4 < a.n);
             if (has_next && (lane == 31 || i4 + 1 >= n4)) {       // its operands came with the float4 (fetch)
                 float m1 = 0.f, v1 = 0.f;
-                nx = step_one<STEP == PAA_STEP_ADAM ? PAA_STEP_NONE : STEP>(raw.np, raw.ng, m1, v1, s);
+                nx = step_one<(STEP & 3) == PAA_STEP_ADAM ? PAA_STEP_NONE : (STEP & 3)>(raw.np, raw.ng, m1, v1, s);
             }
             if (act) acc0 += tv_quad(x, nx, colp, a.T, has_next);
             colp += stepp;
@@ -427,7 +436,7 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
         if (act) r = load_raw4<STEP>(a.p_in, i4 * 4, s);
         if (NORM == NORM_TV && act && (lane == 31 || i4 + 1 >= n4) && i4 * 4 + 4 < a.n) {
             r.np = a.p_in[i4 * 4 + 4];
-            if (STEP != PAA_STEP_NONE) r.ng = ldg1(s, i4 * 4 + 4);
+            if ((STEP & 3) != PAA_STEP_NONE) r.ng = ldg1<STEP>(s, i4 * 4 + 4);
         }
         return r;
     };
@@ -578,10 +587,10 @@ __global__ void __launch_bounds__(kThreads) k_sum_parts(StepDev s, float* out, i
     const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x, nth = (int64_t)gridDim.x * kThreads;
     if (vec) {
         const int64_t n4 = n >> 2;
-        for (int64_t i = tid; i < n4; i += nth) st4(out + i * 4, ldg4(s, i * 4));
-        for (int64_t i = (n4 << 2) + tid; i < n; i += nth) out[i] = ldg1(s, i);
+        for (int64_t i = tid; i < n4; i += nth) st4(out + i * 4, ldg4<kStepParts>(s, i * 4));
+        for (int64_t i = (n4 << 2) + tid; i < n; i += nth) out[i] = ldg1<kStepParts>(s, i);
     } else {
-        for (int64_t i = tid; i < n; i += nth) out[i] = ldg1(s, i);
+        for (int64_t i = tid; i < n; i += nth) out[i] = ldg1<kStepParts>(s, i);
     }
 }
 
@@ -660,6 +669,8 @@ inline int grid_for(const paa_handle* h, int64_t n_vec) {
     return (int)std::max<int64_t>(1, std::min(want, cap));
 }
 
+// template value of a launch: the step mode, plus kStepParts when the gradient has to be summed from several parts
+inline int step_code(int mode, const StepDev& sd) { return mode | ((mode != PAA_STEP_NONE && sd.nparts > 1) ? kStepParts : 0); }
 // every gradient buffer (the one, or all parts) 16-byte aligned
 inline bool grads_aligned(const StepDev& sd) {
     if (!aligned16(sd.grad)) return false;
@@ -670,8 +681,8 @@ inline bool grads_aligned(const StepDev& sd) {
 template <int STEP>
 int launch_step_clamp(paa_handle* h, const float* p_in, float* p_out, int64_t n, float lo, float hi, bool clamp,
                       const StepDev& sd, cudaStream_t st) {
-    bool vec = aligned16(p_in) && aligned16(p_out) && (STEP == PAA_STEP_NONE || grads_aligned(sd)) &&
-               (STEP != PAA_STEP_ADAM || (aligned16(sd.m) && aligned16(sd.v)));
+    bool vec = aligned16(p_in) && aligned16(p_out) && ((STEP & 3) == PAA_STEP_NONE || grads_aligned(sd)) &&
+               ((STEP & 3) != PAA_STEP_ADAM || (aligned16(sd.m) && aligned16(sd.v)));
     int grid = grid_for(h, vec ? (n + 3) / 4 : n);
     if (vec) k_step_clamp<STEP, true><<<grid, kThreads, 0, st>>>(p_in, p_out, n, lo, hi, clamp, sd);
     else k_step_clamp<STEP, false><<<grid, kThreads, 0, st>>>(p_in, p_out, n, lo, hi, clamp, sd);
@@ -738,10 +749,12 @@ int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int
     if (vec && !h->no_coop) {
         // single cooperative launch; fall through to the three-kernel form only if the device refuses it
         void* kern = nullptr;
-        switch (mode) {
+        switch (step_code(mode, sd)) {
             case PAA_STEP_NONE: kern = (void*)k_fused<NORM, PAA_STEP_NONE>; break;
             case PAA_STEP_PGD: kern = (void*)k_fused<NORM, PAA_STEP_PGD>; break;
-            default: kern = (void*)k_fused<NORM, PAA_STEP_ADAM>; break;
+            case PAA_STEP_ADAM: kern = (void*)k_fused<NORM, PAA_STEP_ADAM>; break;
+            case PAA_STEP_PGD | kStepParts: kern = (void*)k_fused<NORM, PAA_STEP_PGD | kStepParts>; break;
+            default: kern = (void*)k_fused<NORM, PAA_STEP_ADAM | kStepParts>; break;
         }
         const int max_grid = 2 * h->num_sms;
         const int64_t work4 = (work + 3) / 4;
@@ -761,10 +774,12 @@ int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int
         h->no_coop = 1;
     }
     int grid = std::min(grid_for(h, vec ? (work + 3) / 4 : work), kMaxPartialBlocks);
-    switch (mode) {
+    switch (step_code(mode, sd)) {
         case PAA_STEP_NONE: rc = launch_reduce<NORM, PAA_STEP_NONE>(h, a, sd, grid, vec, st); break;
         case PAA_STEP_PGD: rc = launch_reduce<NORM, PAA_STEP_PGD>(h, a, sd, grid, vec, st); break;
-        default: rc = launch_reduce<NORM, PAA_STEP_ADAM>(h, a, sd, grid, vec, st); break;
+        case PAA_STEP_ADAM: rc = launch_reduce<NORM, PAA_STEP_ADAM>(h, a, sd, grid, vec, st); break;
+        case PAA_STEP_PGD | kStepParts: rc = launch_reduce<NORM, PAA_STEP_PGD | kStepParts>(h, a, sd, grid, vec, st); break;
+        default: rc = launch_reduce<NORM, PAA_STEP_ADAM | kStepParts>(h, a, sd, grid, vec, st); break;
     }
     if (rc) return rc;
     f.nblocks = grid;
@@ -858,9 +873,11 @@ int paa_step_only(paa_handle* h, const float* p_in, float* p_out, int rows, int 
     if (rc) return rc;
     const int64_t n = (int64_t)rows * T;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (mode) {
+    switch (step_code(mode, sd)) {
         case PAA_STEP_PGD: return launch_step_clamp<PAA_STEP_PGD>(h, p_in, p_out, n, 0.f, 0.f, false, sd, st);
         case PAA_STEP_ADAM: return launch_step_clamp<PAA_STEP_ADAM>(h, p_in, p_out, n, 0.f, 0.f, false, sd, st);
+        case PAA_STEP_PGD | kStepParts: return launch_step_clamp<PAA_STEP_PGD | kStepParts>(h, p_in, p_out, n, 0.f, 0.f, false, sd, st);
+        case PAA_STEP_ADAM | kStepParts: return launch_step_clamp<PAA_STEP_ADAM | kStepParts>(h, p_in, p_out, n, 0.f, 0.f, false, sd, st);
         default: return launch_step_clamp<PAA_STEP_NONE>(h, p_in, p_out, n, 0.f, 0.f, false, sd, st);
     }
 }
@@ -876,9 +893,11 @@ int paa_project_linf(paa_handle* h, const float* p_in, float* p_out, int rows, i
     if (rc) return rc;
     const int64_t n = (int64_t)rows * T;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (mode) {
+    switch (step_code(mode, sd)) {
         case PAA_STEP_PGD: return launch_step_clamp<PAA_STEP_PGD>(h, p_in, p_out, n, (float)lo, (float)hi, true, sd, st);
         case PAA_STEP_ADAM: return launch_step_clamp<PAA_STEP_ADAM>(h, p_in, p_out, n, (float)lo, (float)hi, true, sd, st);
+        case PAA_STEP_PGD | kStepParts: return launch_step_clamp<PAA_STEP_PGD | kStepParts>(h, p_in, p_out, n, (float)lo, (float)hi, true, sd, st);
+        case PAA_STEP_ADAM | kStepParts: return launch_step_clamp<PAA_STEP_ADAM | kStepParts>(h, p_in, p_out, n, (float)lo, (float)hi, true, sd, st);
         default: return launch_step_clamp<PAA_STEP_NONE>(h, p_in, p_out, n, (float)lo, (float)hi, true, sd, st);
     }
 }
