@@ -836,6 +836,7 @@ int paa_make_step(const paa_step* step, int* mode, StepDev* out) {
 
 int paa_launch_adam_prepass(paa_handle* h, const float* p_in, float* p_out, int64_t n, const StepDev& sd, cudaStream_t st) {
     PaaDeviceGuard device_guard(h);
+    if (sd.nparts > 1) return launch_step_clamp<PAA_STEP_ADAM | kStepParts>(h, p_in, p_out, n, 0.f, 0.f, false, sd, st);
     return launch_step_clamp<PAA_STEP_ADAM>(h, p_in, p_out, n, 0.f, 0.f, false, sd, st);
 }
 
