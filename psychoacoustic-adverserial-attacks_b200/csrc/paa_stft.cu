@@ -476,32 +476,44 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     if (SINK == SINK_TIME) sp += ((hop * 4 + 15) / 16) * 16;
     float2* s_fft = (float2*)sp;
     sp += (size_t)kWarps * BufLayout<NFFT>::kFloat2 * sizeof(float2);
+    const unsigned fft_bytes = (unsigned)(kWarps * BufLayout<NFFT>::kFloat2 * sizeof(float2));
     float* s_in = (float*)sp;
     if (SRC == SRC_TIME) sp += (size_t)lin * 4;
-    float* s_ola = (float*)sp;
+    float* s_ola = (float*)sp;                 // overlap-add accumulator (SINK_TIME); before that, where the window visits
 
     const int row = blockIdx.x / a.tiles_per_row, ti = blockIdx.x % a.tiles_per_row;
     // first frame of the tile, and the sample index (unpadded coordinates) of s_in[0]
     const int t0 = (SINK == SINK_TIME) ? ti * S - R / 2 + 1 : ti * FT;
     const int in0 = t0 * hop - NFFT / 2;
 
+    const float* xr = (SRC == SRC_TIME) ? a.x + (size_t)row * a.T : nullptr;
+    const float* gr = (SRC == SRC_TIME && a.grad) ? a.grad + (size_t)row * a.T : nullptr;
+    float* qr = (SRC == SRC_TIME && SINK == SINK_REDUCE && a.q_out) ? a.q_out + (size_t)row * a.T : nullptr;
+    const int own_lo = NFFT / 2, own_hi = NFFT / 2 + FT * hop;   // SINK_REDUCE: samples this tile stores to q_out
+    // Interior tiles (no reflect padding, 16-byte aligned rows) are staged by two TMA bulk copies -- the perturbation
+    // span straight into s_in, the gradient span into the still idle FFT buffers -- issued by one thread before
+    // anything else; a shared-memory pass then applies the PGD step in place.  Row-end tiles take the per-thread path.
+    const bool tma_stage = SRC == SRC_TIME && a.vec_ok && in0 >= 0 && in0 + lin <= a.T && (!gr || (unsigned)lin * 4u <= fft_bytes);
+
     if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (tid == 0) {
-        // tables stay; the window lands in the (still idle) FFT buffers: every lane copies its 16 values to
-        // registers and the envelope table is derived from it before the first frame overwrites it
-        mbar_expect_tx(&bar, tbl_bytes + (a.blob_bytes - a.off_win) + (SINK == SINK_REDUCE ? a.fm_blob_bytes : 0u));
+        // tables stay; the window only visits (it lands where the overlap-add accumulator will be): every lane copies
+        // its 16 values to registers and the envelope table is derived from it before the accumulator is zeroed
+        const unsigned win_bytes = a.blob_bytes - a.off_win;
+        mbar_expect_tx(&bar, tbl_bytes + win_bytes + (SINK == SINK_REDUCE ? a.fm_blob_bytes : 0u) +
+                                 (tma_stage ? (unsigned)lin * 4u * (gr ? 2u : 1u) : 0u));
         tma_bulk_g2s(smem, a.blob, tbl_bytes, &bar);
-        tma_bulk_g2s(s_fft, (const unsigned char*)a.blob + a.off_win, a.blob_bytes - a.off_win, &bar);
+        tma_bulk_g2s(s_ola, (const unsigned char*)a.blob + a.off_win, win_bytes, &bar);
         if (SINK == SINK_REDUCE) tma_bulk_g2s(s_thr, a.fm_blob, a.fm_blob_bytes, &bar);
+        if (tma_stage) {
+            tma_bulk_g2s(s_in, xr + in0, (unsigned)lin * 4u, &bar);
+            if (gr) tma_bulk_g2s(s_fft, gr + in0, (unsigned)lin * 4u, &bar);
+        }
     }
 
     // ---- stage the input span (reflect padding at the row ends, PGD step fused) ----------------
-    if (SRC == SRC_TIME) {
-        const float* xr = a.x + (size_t)row * a.T;
-        const float* gr = a.grad ? a.grad + (size_t)row * a.T : nullptr;
-        float* qr = (SINK == SINK_REDUCE && a.q_out) ? a.q_out + (size_t)row * a.T : nullptr;
-        const int own_lo = NFFT / 2, own_hi = NFFT / 2 + FT * hop;   // SINK_REDUCE: samples this tile stores to q_out
+    if (SRC == SRC_TIME && !tma_stage) {
         const int T = a.T;
         // All global loads of a chunk are issued before any of them is consumed (kStageUnroll x 2 float4 in flight
         // per thread): the staging latency is otherwise exposed once per loop trip.
@@ -555,8 +567,6 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
             }
         }
     }
-    if (SINK == SINK_TIME)
-        for (int i4 = tid; i4 < S * hop / 4; i4 += kThreadsStft) *reinterpret_cast<float4*>(s_ola + i4 * 4) = make_float4(0, 0, 0, 0);
     // The tile this slot's next CTA will stage: pull it from HBM into L2 now, so that its (latency-bound) prologue
     // finds the lines there.  Reflect-padding samples at the row ends are left to the demand loads.
     if (SRC == SRC_TIME && a.pf_stride > 0) {
@@ -596,9 +606,26 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     mbar_wait(&bar, 0);
     // this lane's slice of the (halved) window lives in registers for the whole tile: the first forward stage and the
     // last inverse stage touch the same points m = lane + 32*j, j = 0 .. N/32-1 (saves 64 smem wavefronts per frame)
+    if (tma_stage && gr) {
+        // PGD step on the staged span, in shared memory (the gradient sits in the FFT buffers)
+        const float4* g4 = reinterpret_cast<const float4*>(s_fft);
+        float4* p4 = reinterpret_cast<float4*>(s_in);
+        const float lr = a.lr;
+        for (int i4 = tid; i4 < lin / 4; i4 += kThreadsStft) {
+            float4 v = p4[i4];
+            const float4 g = g4[i4];
+            v.x += lr * ((float)(g.x > 0.f) - (float)(g.x < 0.f));
+            v.y += lr * ((float)(g.y > 0.f) - (float)(g.y < 0.f));
+            v.z += lr * ((float)(g.z > 0.f) - (float)(g.z < 0.f));
+            v.w += lr * ((float)(g.w > 0.f) - (float)(g.w < 0.f));
+            p4[i4] = v;
+            const int i = i4 * 4;
+            if (qr && i >= own_lo && i < own_hi) *reinterpret_cast<float4*>(qr + in0 + i) = v;
+        }
+    }
     cpx wreg[N / 32];
     {
-        const float* s_win = reinterpret_cast<const float*>(s_fft);      // visiting copy, overwritten by the first FFT
+        const float* s_win = s_ola;                                      // visiting copy, zeroed / unused afterwards
         const cpx* win2 = reinterpret_cast<const cpx*>(s_win);
 #pragma unroll
         for (int j = 0; j < N / 32; ++j) wreg[j] = win2[lane + 32 * j];
@@ -611,6 +638,10 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
         }
     }
     __syncthreads();
+    if (SINK == SINK_TIME) {
+        for (int i4 = tid; i4 < S * hop / 4; i4 += kThreadsStft) *reinterpret_cast<float4*>(s_ola + i4 * 4) = make_float4(0, 0, 0, 0);
+        __syncthreads();
+    }
 
     // ---- frames ----------------------------------------------------------------------------------
     cpx* buf = reinterpret_cast<cpx*>(s_fft) + (size_t)warp * BufLayout<NFFT>::kFloat2;
@@ -874,7 +905,8 @@ size_t smem_bytes(const paa_handle* h, int src, int sink, int op, int FT, int S)
     if (sink == SINK_REDUCE) b += h->fm_blob_bytes;
     b += (size_t)kWarps * BufLayout<NFFT>::kFloat2 * sizeof(float2);
     if (src == SRC_TIME) b += (size_t)((FT - 1) * h->hop + NFFT) * 4;
-    if (sink == SINK_TIME) b += (size_t)S * h->hop * 4;
+    // overlap-add accumulator, or just the window's visiting place (at least n_fft floats either way)
+    b += sink == SINK_TIME ? std::max((size_t)S * h->hop * 4, (size_t)NFFT * 4) : (size_t)NFFT * 4;
     return b;
 }
 
