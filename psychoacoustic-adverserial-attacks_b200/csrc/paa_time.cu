@@ -604,15 +604,33 @@ __global__ void __launch_bounds__(kThreads) k_compose(const float* __restrict__ 
     const int W = VEC ? 4 : 1;
     const int cols = (T + W - 1) / W;
     for (int c = blockIdx.x * kThreads + threadIdx.x; c < cols; c += gridDim.x * kThreads) {
-        for (int b = blockIdx.y; b < rows; b += gridDim.y) {
-            const size_t i = (size_t)b * T + (size_t)c * W, pi = (p_rows == 1 ? 0 : (size_t)b * T) + (size_t)c * W;
-            if (VEC) {
-                float4 x = ld4_stream(clean + i);
-                const float4 q = ld4(p + pi);
-                x.x = clamp1(x.x + q.x, -1.f, 1.f); x.y = clamp1(x.y + q.y, -1.f, 1.f);
-                x.z = clamp1(x.z + q.z, -1.f, 1.f); x.w = clamp1(x.w + q.w, -1.f, 1.f);
-                st4(out + i, x);
-            } else {
+        if (VEC) {
+            // four rows per trip, all loads issued before the first store (memory-level parallelism)
+            constexpr int U = 4;
+            for (int b0 = blockIdx.y; b0 < rows; b0 += U * gridDim.y) {
+                float4 x[U], q[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int b = b0 + u * gridDim.y;
+                    if (b < rows) {
+                        x[u] = ld4_stream(clean + (size_t)b * T + (size_t)c * 4);
+                        q[u] = (p_rows == 1 && u > 0) ? q[0] : ld4(p + (p_rows == 1 ? 0 : (size_t)b * T) + (size_t)c * 4);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int b = b0 + u * gridDim.y;
+                    if (b < rows) {
+                        float4 v = x[u];
+                        v.x = clamp1(v.x + q[u].x, -1.f, 1.f); v.y = clamp1(v.y + q[u].y, -1.f, 1.f);
+                        v.z = clamp1(v.z + q[u].z, -1.f, 1.f); v.w = clamp1(v.w + q[u].w, -1.f, 1.f);
+                        st4(out + (size_t)b * T + (size_t)c * 4, v);
+                    }
+                }
+            }
+        } else {
+            for (int b = blockIdx.y; b < rows; b += gridDim.y) {
+                const size_t i = (size_t)b * T + (size_t)c * W, pi = (p_rows == 1 ? 0 : (size_t)b * T) + (size_t)c * W;
                 out[i] = clamp1(clean[i] + p[pi], -1.f, 1.f);
             }
         }
@@ -636,7 +654,7 @@ __global__ void __launch_bounds__(kThreads) k_compose_bwd(const float* __restric
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
             if (VEC) q = ld4(p + (size_t)c * 4); else q.x = p[c];
-#pragma unroll 4
+#pragma unroll 8
             for (int b = 0; b < rows; ++b) {
                 const size_t i = (size_t)b * T + (size_t)c * W;
                 if (VEC) {
