@@ -3,14 +3,17 @@
 // A real frame of n_fft samples is transformed as a complex FFT of N = n_fft/2 points
 // (z[m] = x[2m] + i x[2m+1]) followed by the usual split into the n_fft/2+1 one-sided bins.
 // The complex FFT is a three-stage Stockham autosort (radix 8*8*8 for N=512, 4*8*8 for N=256):
-// every lane owns N/32 points per stage in registers, stages exchange through a warp-private
-// shared-memory buffer of float2, and only __syncwarp is needed.
+// every lane owns N/32 points per stage in registers -- each complex point one 64-bit register pair, all arithmetic
+// in sm_100a's packed fp32 instructions (FADD2 / FMUL2 / FFMA2, see "packed complex arithmetic" below) -- stages
+// exchange through a warp-private shared-memory buffer, and only __syncwarp is needed.
 //
-// Buffer layout: logical point i lives at pad(i) = i + (i >> 4) (one spare slot per 16).  The pad is additive, so
-// every access of a stage is  (one per-lane base register) + (compile-time offset)  and costs no
-// address arithmetic; the contiguous loads stay conflict free and the strided stores of the first
-// two stages are at worst 2-way conflicted (tools/bank_search.py).  The kernel is issue-bound, not
-// shared-memory-bandwidth bound, which is why this beats a conflict-free XOR swizzle here.
+// Buffer layout: the two exchanges use two additive paddings of the point index (padc, Plan::padB).  Additive means
+// every access of a stage is  (one per-lane base register) + (compile-time offset)  and costs no address arithmetic;
+// both make every load and store of their exchange bank-conflict free (tools/bank_search.py conventions: a 64-bit
+// access is served per half-warp, conflict free when 16 lanes hit 16 distinct 8-byte slots mod 16).
+//
+// n_fft 1024 additionally has a "paired" form of the last forward / first inverse stage (paired_j1 below) that
+// leaves the spectrum in registers with both members of every conjugate pair in the same thread.
 #pragma once
 #include <cuda_runtime.h>
 

@@ -9,12 +9,15 @@
 // Geometry.  centre=True: frame t covers samples [t*hop - n/2, t*hop + n/2) of the reflect-padded
 // row; output sample n receives the R = n_fft/hop frames t in (n/hop + R/2 - R, n/hop + R/2].
 // A CTA of 8 warps owns S = FT-R+1 consecutive output hop-blocks and transforms the FT = 8*R*Q
-// frames that touch them (R-1 halo frames are recomputed by the neighbour tile).  The input span
-// is staged once in shared memory (float4 loads, reflect at the row ends, PGD step applied on
-// the fly), every warp runs whole frames (paa_fft.cuh), and the inverse frames are overlap-added
-// into a shared accumulator in R phases: frames with equal t mod R never overlap, so plain
+// frames that touch them (R-1 halo frames are recomputed by the neighbour tile).  The input span is staged once in
+// shared memory -- interior tiles by two TMA bulk copies (cp.async.bulk + mbarrier: the perturbation span into the
+// tile buffer, the gradient span into the still idle FFT buffers, then a shared-memory pass applies the PGD step),
+// row-end tiles by float4 loads with reflect padding -- while the CTA prefetches the next tile of its slot into L2.
+// Every warp runs whole frames (paa_fft.cuh, packed-fp32 complex arithmetic); for n_fft 1024 the spectrum stays in
+// registers between the forward and the inverse transform (paired butterflies, middle_paired).  The inverse frames
+// are overlap-added into a shared accumulator in R phases: frames with equal t mod R never overlap, so plain
 // read-modify-write is race free and the summation order is fixed (deterministic output).
-// Window / twiddle tables arrive by one 1-D TMA bulk copy (cp.async.bulk + mbarrier).
+// Twiddle tables and the window arrive by the same mbarrier-tracked TMA bulk copies.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
