@@ -152,6 +152,24 @@ def test_oracle_differential(norm, sigma, over, rows, B, T, env):
     close(paa.step_and_project(p.cuda(), grad.cuda(), clean.cuda(), args, env["it_gpu"], thr_g), want)
 
 
+@pytest.mark.parametrize("norm,sigma", [("max_phon", 0.03), ("min_max_freqs", 0.01), ("fletcher_munson", 0.1)])
+@pytest.mark.parametrize("T", [50000, 65536])
+def test_long_rows_interior_tiles(norm, sigma, T, env):
+    """Rows long enough for several interior tiles (staged by TMA bulk copies, paired-butterfly middle) next to the
+    row-end tiles (per-thread staging with reflect padding): PGD-fused parity against the oracle."""
+    orc, paa = env["orc"], env["paa"]
+    g = torch.Generator().manual_seed(T)
+    clean = (torch.rand(2, T, generator=g) * 2 - 1) * 0.1
+    p = torch.randn(2, T, generator=g) * sigma
+    grad = torch.randn(2, T, generator=g)
+    grad[torch.rand(2, T, generator=g) < 0.01] = 0.0
+    hp = orc.Hyper(norm_type=norm, optimizer_type="pgd")
+    args = make_args(hp)
+    thr_c, thr_g = orc.phon_threshold(hp.n_fft, hp.sr, hp.max_phon_level), thr_gpu(args)
+    want = orc.step_and_constrain(p, grad, clean, hp, env["it_cpu"], thr_c)
+    close(paa.step_and_project(p.cuda(), grad.cuda(), clean.cuda(), args, env["it_gpu"], thr_g), want)
+
+
 def test_fm_identity_roundtrip_option(env):
     orc, paa = env["orc"], env["paa"]
     g = torch.Generator().manual_seed(5)
