@@ -459,6 +459,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ float red[kWarps];
+    __shared__ int s_done[kWarps];             // overlap-add phases each warp has completed (SINK_TIME)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hop = a.hop, R = a.R, FT = a.frames_per_tile;
@@ -499,6 +500,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     const bool tma_stage = SRC == SRC_TIME && a.vec_ok && in0 >= 0 && in0 + lin <= a.T && (!gr || (unsigned)lin * 4u <= fft_bytes);
 
     if (tid == 0) mbar_init(&bar, 1);
+    if (tid < kWarps) s_done[tid] = 0;
     __syncthreads();
     if (tid == 0) {
         // tables stay; the window only visits (it lands where the overlap-add accumulator will be): every lane copies
@@ -673,8 +675,32 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
             const int obase = (f - R + 1) * hop;                     // owned-region coordinate of frame sample 0
             cpx* ola = reinterpret_cast<cpx*>(s_ola + obase) + lane;   // only dereferenced inside [0, olim)
             const bool inside = obase >= 0 && obase + NFFT <= olim;  // warp-uniform: the whole frame lands in the owned region
-            auto ola_all = [&](int, int c, cpx v) { ola[c] = fma2(v, wreg[c / 32], ola[c]); };
+            // Overlap-add ordering without block barriers.  Frames that touch the same accumulator samples are at most
+            // R-1 apart, i.e. they belong to this warp (program order) or to a neighbouring warp and another phase;
+            // adding them in phase order only requires that warp w+1 has finished phase r-1 before warp w adds phase r
+            // (the mirror case, warp w-1 in a later phase, waits on this warp by the same rule).  So the warps run
+            // skewed instead of in lock-step, and every sample still receives its R contributions in the same fixed
+            // order.  The wait sits in front of the first accumulator access of the frame (c == 0).
+            auto wait_neighbour = [&]() {
+                if (r > 0 && warp + 1 < kWarps) {
+                    if (lane == 0) {
+                        int done;
+                        do {
+                            asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(done) : "r"(smem_u32(&s_done[warp + 1])) : "memory");
+                        } while (done < r);
+                    }
+                    __syncwarp();
+                }
+            };
+            // max_phon sits at the 128-register ceiling: there the wait goes in front of the whole inverse transform
+            // (measured: the late wait costs it a spill and 1.4 %, and gains the other operators 3 %)
+            constexpr bool kLateWait = OP != OP_PHON;
+            auto ola_all = [&](int, int c, cpx v) {
+                if (kLateWait && c == 0) wait_neighbour();
+                ola[c] = fma2(v, wreg[c / 32], ola[c]);
+            };
             auto ola_edge = [&](int m, int c, cpx v) {
+                if (kLateWait && c == 0) wait_neighbour();
                 const int o = obase + 2 * m;
                 if (o >= 0 && o < olim) ola[c] = fma2(v, wreg[c / 32], ola[c]);
             };
@@ -694,6 +720,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
                     slow = true;
                 }
                 if (SINK == SINK_TIME) {
+                    if (!kLateWait) wait_neighbour();
                     if (inside) fft_inverse_paired(buf, s_tw, tw1, lane, lb, z, ola_all);
                     else fft_inverse_paired(buf, s_tw, tw1, lane, lb, z, ola_edge);
                 }
@@ -714,6 +741,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
                     __syncwarp();
                 }
                 if (SINK == SINK_TIME) {
+                    if (!kLateWait) wait_neighbour();
                     __syncwarp();
                     auto from_buf = [&](int, int c) { return buf[lane + c]; };
                     if (inside) fft_warp<NFFT, +1>(buf, s_tw, tw1, lane, lb, from_buf, ola_all);
@@ -721,8 +749,12 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
                 }
             }
         }
-        if (SINK == SINK_TIME) __syncthreads();                  // next phase overlaps these frames
+        if (SINK == SINK_TIME) {                                 // publish: this warp's phase-r contributions are in place
+            __syncwarp();
+            if (lane == 0) asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(&s_done[warp])), "r"(r + 1) : "memory");
+        }
     }
+    if (SINK == SINK_TIME) __syncthreads();                      // the epilogue reads every warp's samples
 
     // ---- epilogue -----------------------------------------------------------------------------------
     if (SINK == SINK_TIME) {
