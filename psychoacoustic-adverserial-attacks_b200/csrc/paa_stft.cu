@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     const unsigned fft_bytes = (unsigned)(kWarps * BufLayout<NFFT>::kFloat2 * sizeof(float2));
     float* s_in = (float*)sp;
     if (SRC == SRC_TIME) sp += (size_t)lin * 4;
-    float* s_ola = (float*)sp;                 // overlap-add accumulator (SINK_TIME); before that, where the window visits
+    float* s_ola = (float*)sp;                 // overlap-add accumulator (SINK_TIME)
 
     const int row = blockIdx.x / a.tiles_per_row, ti = blockIdx.x % a.tiles_per_row;
     // first frame of the tile, and the sample index (unpadded coordinates) of s_in[0]
@@ -503,13 +503,11 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     if (tid < kWarps) s_done[tid] = 0;
     __syncthreads();
     if (tid == 0) {
-        // tables stay; the window only visits (it lands where the overlap-add accumulator will be): every lane copies
-        // its 16 values to registers and the envelope table is derived from it before the accumulator is zeroed
-        const unsigned win_bytes = a.blob_bytes - a.off_win;
-        mbar_expect_tx(&bar, tbl_bytes + win_bytes + (SINK == SINK_REDUCE ? a.fm_blob_bytes : 0u) +
+        // the FFT twiddles stay resident; the window never enters shared memory (every lane keeps its 16 values in
+        // registers, read once from the L2-resident table while the bulk copies are in flight)
+        mbar_expect_tx(&bar, tbl_bytes + (SINK == SINK_REDUCE ? a.fm_blob_bytes : 0u) +
                                  (tma_stage ? (unsigned)lin * 4u * (gr ? 2u : 1u) : 0u));
         tma_bulk_g2s(smem, a.blob, tbl_bytes, &bar);
-        tma_bulk_g2s(s_ola, (const unsigned char*)a.blob + a.off_win, win_bytes, &bar);
         if (SINK == SINK_REDUCE) tma_bulk_g2s(s_thr, a.fm_blob, a.fm_blob_bytes, &bar);
         if (tma_stage) {
             tma_bulk_g2s(s_in, xr + in0, (unsigned)lin * 4u, &bar);
@@ -572,6 +570,23 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
             }
         }
     }
+    // this lane's slice of the (halved) window lives in registers for the whole tile: the first forward stage and the
+    // last inverse stage touch the same points m = lane + 32*j, j = 0 .. N/32-1 (saves 64 smem wavefronts per frame)
+    cpx wreg[N / 32];
+    {
+        const float* g_w = reinterpret_cast<const float*>((const unsigned char*)a.blob + a.off_win);
+        const float2* g_w2 = reinterpret_cast<const float2*>(g_w);
+#pragma unroll
+        for (int j = 0; j < N / 32; ++j) { const float2 w = __ldg(g_w2 + lane + 32 * j); wreg[j] = pk(w.x, w.y); }
+        if (SINK == SINK_TIME) {
+            for (int q = tid; q < hop; q += kThreadsStft) {
+                float e = 0.f;
+                for (int d = R - 1; d >= 0; --d) { const float wv = 2.f * __ldg(g_w + d * hop + q); e += wv * wv; }
+                s_renv[q] = 1.f / e;
+            }
+            for (int i4 = tid; i4 < S * hop / 4; i4 += kThreadsStft) *reinterpret_cast<float4*>(s_ola + i4 * 4) = make_float4(0, 0, 0, 0);
+        }
+    }
     // The tile this slot's next CTA will stage: pull it from HBM into L2 now, so that its (latency-bound) prologue
     // finds the lines there.  Reflect-padding samples at the row ends are left to the demand loads.
     if (SRC == SRC_TIME && a.pf_stride > 0) {
@@ -609,8 +624,6 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
         }
     }
     mbar_wait(&bar, 0);
-    // this lane's slice of the (halved) window lives in registers for the whole tile: the first forward stage and the
-    // last inverse stage touch the same points m = lane + 32*j, j = 0 .. N/32-1 (saves 64 smem wavefronts per frame)
     if (tma_stage && gr) {
         // PGD step on the staged span, in shared memory (the gradient sits in the FFT buffers)
         const float4* g4 = reinterpret_cast<const float4*>(s_fft);
@@ -628,25 +641,7 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
             if (qr && i >= own_lo && i < own_hi) *reinterpret_cast<float4*>(qr + in0 + i) = v;
         }
     }
-    cpx wreg[N / 32];
-    {
-        const float* s_win = s_ola;                                      // visiting copy, zeroed / unused afterwards
-        const cpx* win2 = reinterpret_cast<const cpx*>(s_win);
-#pragma unroll
-        for (int j = 0; j < N / 32; ++j) wreg[j] = win2[lane + 32 * j];
-        if (SINK == SINK_TIME) {
-            for (int q = tid; q < hop; q += kThreadsStft) {
-                float e = 0.f;
-                for (int d = R - 1; d >= 0; --d) { const float wv = 2.f * s_win[d * hop + q]; e += wv * wv; }
-                s_renv[q] = 1.f / e;
-            }
-        }
-    }
     __syncthreads();
-    if (SINK == SINK_TIME) {
-        for (int i4 = tid; i4 < S * hop / 4; i4 += kThreadsStft) *reinterpret_cast<float4*>(s_ola + i4 * 4) = make_float4(0, 0, 0, 0);
-        __syncthreads();
-    }
 
     // ---- frames ----------------------------------------------------------------------------------
     cpx* buf = reinterpret_cast<cpx*>(s_fft) + (size_t)warp * BufLayout<NFFT>::kFloat2;
@@ -940,8 +935,7 @@ size_t smem_bytes(const paa_handle* h, int src, int sink, int op, int FT, int S)
     if (sink == SINK_REDUCE) b += h->fm_blob_bytes;
     b += (size_t)kWarps * BufLayout<NFFT>::kFloat2 * sizeof(float2);
     if (src == SRC_TIME) b += (size_t)((FT - 1) * h->hop + NFFT) * 4;
-    // overlap-add accumulator, or just the window's visiting place (at least n_fft floats either way)
-    b += sink == SINK_TIME ? std::max((size_t)S * h->hop * 4, (size_t)NFFT * 4) : (size_t)NFFT * 4;
+    if (sink == SINK_TIME) b += (size_t)S * h->hop * 4;
     return b;
 }
 
