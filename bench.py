@@ -47,8 +47,8 @@ SNR_DB = 40.0
 LR = 1e-4
 UNTARGETED_TEXT = "hello world this is a test"
 METRIC = "attack audio-sec/s per PGD step"
-# one `ncu --set full` capture of the dominant kernel at this workload (profiles/r01g_ncu_full.txt), bytes per launch
-NCU_TRAFFIC_BYTES = 63_878_400
+# one `ncu --set full` capture of the dominant kernel at this workload (profiles/r01h_ncu_full.txt), bytes per launch
+NCU_TRAFFIC_BYTES = 63_775_744
 
 
 def measured_peak():
@@ -266,8 +266,8 @@ def run_ours(a):
         "roofline": {"bound": "hbm", "kernel": "k_fused<snr,pgd>: PGD step + energy reduce + grid barrier + rescale, one cooperative launch",
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": NCU_TRAFFIC_BYTES if rows == BATCH else None, "algorithmic_bytes": nbytes,
-                     "traffic_source": "profiles/r01g_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum of "
-                                       "k_fused<1,1> (61.49 + 2.39 MB; the 20.5 MB result is still in L2 at kernel end)", "avg_call_us": round(proj_ms * 1e3, 2),
+                     "traffic_source": "profiles/r01h_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum of "
+                                       "k_fused<1,1> (61.49 + 2.29 MB; the 20.5 MB result is still in L2 at kernel end)", "avg_call_us": round(proj_ms * 1e3, 2),
                      "peak_source": peak_src},
         "wer_counters": {"errors": int(counters[0]), "ref_words": int(counters[1])},
         "loss_last": round(float(losses[-1]), 3),
