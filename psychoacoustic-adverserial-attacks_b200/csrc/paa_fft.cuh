@@ -40,16 +40,18 @@ template <int NFFT> struct BufLayout {
     static constexpr int kFloat2 = ((Plan<NFFT>::padB(Plan<NFFT>::N - 1) + 2) / 2) * 2;      // padB is the wider of the two
 };
 
-// per-lane twiddle table: stage 1 block [4][32] (k = j mod R0 does not depend on b) then stage 2 block
-// [NB2][4][32], float4 entries holding the forward twiddles (cos, -sin) of r = 2q and r = 2q+1
+// per-lane twiddle tables.  Stage 1: one [4][32] block of float4 (k = j mod R0 does not depend on b), the forward
+// twiddles (cos, -sin) of r = 2q and r = 2q+1, kept in registers by the kernel.  Stage 2 (compact): per block
+// (b = 0, b = 1, and for n_fft 1024 the paired b = 1) only W^k, W^2k, W^4k as float2 [3][32]; the other four powers
+// are products of two of them (W^3k = W^k W^2k, W^5k = W^k W^4k, W^6k = W^2k W^4k, W^7k = W^3k W^4k: at most two
+// extra roundings) -- 8 packed instructions per block instead of 10 more shared-memory wavefronts.
 template <int NFFT> struct TwLayout {
     using P = Plan<NFFT>;
     static constexpr int NB1 = P::N / P::R1 / 32, NB2 = P::N / P::R2 / 32;
     static constexpr int kStage1 = 4 * 32;               // float4 entries
-    static constexpr int kStage2 = NB2 * 4 * 32;
-    // n_fft 1024 only: one more [4][32] block, the last-stage twiddles of the "paired" butterfly j1(lane) below
-    static constexpr int kStage2Paired = (NFFT == 1024) ? 4 * 32 : 0;
-    static constexpr int kTotal = kStage1 + kStage2 + kStage2Paired;
+    static constexpr int kStage2Blocks = NB2 + ((NFFT == 1024) ? 1 : 0);
+    static constexpr int kStage2 = kStage2Blocks * 3 * 32 / 2;          // float4 entries (3 x 32 float2 per block)
+    static constexpr int kTotal = kStage1 + kStage2;
 };
 
 // Paired butterfly assignment (n_fft 1024, N = 512 = 8*8*8).  The last forward stage and the first inverse stage
@@ -91,6 +93,11 @@ __device__ __forceinline__ cpx rot90(cpx v) {
 template <int DIR>
 __device__ __forceinline__ cpx cmul_tw(cpx v, float wx, float wy) {
     return fma2(rot90<-DIR>(v), bcast(wy), mul2(v, bcast(wx)));
+}
+
+// product of two complex numbers (used to derive twiddle powers: the product of two forward twiddles is one)
+__device__ __forceinline__ cpx cmul(cpx a, cpx b) {
+    return fma2(rot90<+1>(a), bcast(cim(b)), mul2(a, bcast(cre(b))));
 }
 
 template <int DIR>
@@ -230,18 +237,24 @@ __device__ __forceinline__ void fft_stage2(const cpx* buf, const float4* __restr
     using P = Plan<NFFT>;
     using L = TwLayout<NFFT>;
     constexpr int N = P::N, R = P::R2, NB = N / R / 32;
-    const float4* t2 = tw + L::kStage1;
+    const float2* t2 = reinterpret_cast<const float2*>(tw + L::kStage1);
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
             v[b][r] = (PAIRED && b == 1) ? buf[lb.ldB1 + P::padB(r * (N / R))] : buf[lb.ldB + P::padB(32 * b + r * (N / R))];
-#pragma unroll
-        for (int q = 0; q < R / 2; ++q) {
-            const float4 w = t2[(((PAIRED && b == 1) ? 2 : b) * 4 + q) * 32 + lane];
-            if (q > 0) v[b][2 * q] = cmul_tw<DIR>(v[b][2 * q], w.x, w.y);
-            v[b][2 * q + 1] = cmul_tw<DIR>(v[b][2 * q + 1], w.z, w.w);
-        }
+        // twiddles W^{k r}, r = 1..7, from W^k, W^2k, W^4k
+        const float2* tb = t2 + ((PAIRED && b == 1) ? 2 : b) * 96 + lane;
+        const float2 f1 = tb[0], f2 = tb[32], f4 = tb[64];
+        const cpx w1 = pk(f1.x, f1.y), w2 = pk(f2.x, f2.y), w4 = pk(f4.x, f4.y);
+        const cpx w3 = cmul(w1, w2), w5 = cmul(w1, w4), w6 = cmul(w2, w4), w7 = cmul(w3, w4);
+        v[b][1] = cmul_tw<DIR>(v[b][1], cre(w1), cim(w1));
+        v[b][2] = cmul_tw<DIR>(v[b][2], cre(w2), cim(w2));
+        v[b][3] = cmul_tw<DIR>(v[b][3], cre(w3), cim(w3));
+        v[b][4] = cmul_tw<DIR>(v[b][4], cre(w4), cim(w4));
+        v[b][5] = cmul_tw<DIR>(v[b][5], cre(w5), cim(w5));
+        v[b][6] = cmul_tw<DIR>(v[b][6], cre(w6), cim(w6));
+        v[b][7] = cmul_tw<DIR>(v[b][7], cre(w7), cim(w7));
         Dft<R, DIR>::run(v[b]);
     }
 }

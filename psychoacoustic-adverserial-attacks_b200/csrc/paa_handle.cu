@@ -39,17 +39,19 @@ template <int NFFT>
 void build_tables(std::vector<float>& tw, std::vector<float>& post) {
     using P = paa::Plan<NFFT>;
     stage_twiddles(tw, P::N, P::R1, P::R0);
-    stage_twiddles(tw, P::N, P::R2, P::R0 * P::R1);
-    if (NFFT == 1024) {
-        // last-stage twiddles of the paired butterfly j1(lane) (paa_fft.cuh): W_N^{j1 r}, same [q][lane] float4 layout
-        for (int q = 0; q < 4; ++q)
-            for (int lane = 0; lane < 32; ++lane)
-                for (int r = 2 * q; r < 2 * q + 2; ++r) {
-                    const double th = 2.0 * M_PI * (double)paa::paired_j1(lane) * (double)r / (double)P::N;
-                    tw.push_back((float)std::cos(th));
-                    tw.push_back((float)(-std::sin(th)));
-                }
-    }
+    // stage 2, compact: W_N^{k e} for e = 1, 2, 4 as float2 [block][e][lane]; blocks: b = 0 .. NB2-1 (k = lane + 32 b)
+    // and, for n_fft 1024, the paired butterfly k = j1(lane) (paa_fft.cuh)
+    static_assert(P::R2 == 8, "the compact stage-2 table assumes a radix-8 last stage");
+    auto block = [&](auto kof) {
+        for (int e : {1, 2, 4})
+            for (int lane = 0; lane < 32; ++lane) {
+                const double th = 2.0 * M_PI * (double)kof(lane) * (double)e / (double)P::N;
+                tw.push_back((float)std::cos(th));
+                tw.push_back((float)(-std::sin(th)));
+            }
+    };
+    for (int b = 0; b < P::N / P::R2 / 32; ++b) block([b](int lane) { return lane + 32 * b; });
+    if (NFFT == 1024) block([](int lane) { return paa::paired_j1(lane); });
     for (int k = 0; k <= P::N / 2; ++k) {
         const double th = 2.0 * M_PI * (double)k / (double)NFFT;
         post.push_back((float)std::cos(th));
