@@ -13,7 +13,9 @@ bit-identical perturbations, nothing but the partials crosses the links, and the
 Buffers are double buffered by step parity, so one barrier per step is enough: a rank can only be two steps ahead of a
 peer that still reads a slot after it has passed the barrier in between, which that peer joins after its read.
 
-``backend="nccl"`` is the plain baseline (all-reduce, then the ordinary kernels on the reduced buffers)."""
+``backend="nccl"`` is the plain baseline (all-reduce, then the ordinary kernels on the reduced buffers);
+``backend="auto"`` takes the peer-memory path when the rendezvous succeeds on every rank and the baseline otherwise."""
+import logging
 from typing import Optional
 
 import torch
@@ -57,17 +59,35 @@ class UniversalExchange:
         self.step = 0
         self._numel_cache = {}
         self._keep = None
-        if backend == "symmetric":
-            import torch.distributed._symmetric_memory as symm
-            self.buf = symm.empty(2 * self.slot, dtype=torch.float32, device=device)
-            self.hdl = symm.rendezvous(self.buf, self.group.group_name)
-            self.ptrs = [int(x) for x in self.hdl.buffer_ptrs]
-            self.buf.zero_()
+        if backend == "auto":
+            # peer-memory exchange when the box supports it (NVLink P2P + symmetric memory), else the NCCL baseline.
+            # Every rank must take the same branch: the outcome of the rendezvous is agreed on with one all-reduce.
+            try:
+                self._init_symmetric()
+                ok = 1
+            except Exception as exc:                                    # noqa: BLE001
+                logging.getLogger("asr_attack").warning("mode U: symmetric memory unavailable (%s); using NCCL", exc)
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            backend = self.backend = "symmetric" if int(flag.item()) == 1 else "nccl"
+            if backend == "nccl":
+                self.buf = torch.zeros(2 * self.slot, dtype=torch.float32, device=device)
+                self.hdl, self.ptrs = None, None
+        elif backend == "symmetric":
+            self._init_symmetric()
         elif backend == "nccl":
             self.buf = torch.zeros(2 * self.slot, dtype=torch.float32, device=device)
             self.hdl, self.ptrs = None, None
         else:
             raise ValueError(f"unknown backend {backend!r}")
+
+    def _init_symmetric(self) -> None:
+        import torch.distributed._symmetric_memory as symm
+        self.buf = symm.empty(2 * self.slot, dtype=torch.float32, device=self.device)
+        self.hdl = symm.rendezvous(self.buf, self.group.group_name)
+        self.ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+        self.buf.zero_()
 
     def _global_numel(self, clean: torch.Tensor) -> int:
         key = tuple(clean.shape)
