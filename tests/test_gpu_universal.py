@@ -106,7 +106,7 @@ def _oracle(optimizer):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="mode U needs two GPUs")
-@pytest.mark.parametrize("backend,optimizer", [("symmetric", "pgd"), ("symmetric", "adam"), ("nccl", "pgd")])
+@pytest.mark.parametrize("backend,optimizer", [("symmetric", "pgd"), ("symmetric", "adam"), ("nccl", "pgd"), ("auto", "pgd")])
 def test_universal_two_ranks_match_single_process_oracle(backend, optimizer):
     from conftest import rel_max
     got = _run(backend, optimizer)
