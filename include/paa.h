@@ -100,8 +100,9 @@ int paa_last_cuda_error(const paa_handle* h);        /* cudaError_t of the last 
 int paa_num_bins(const paa_handle* h);                /* F = n_fft/2+1                            */
 int paa_num_frames(const paa_handle* h, int T);       /* T' = 1 + T/hop (centre=True)             */
 /* Scratch a call needs.  rows = T = 0: the reducing time-domain projections (l2, snr, tv) and the paa_spec_fm_*
- * functions (scalars + block partials, ~128 KB).  rows, T > 0: the STFT-domain projections, which add a [rows, T]
- * fp32 staging buffer (used by an Adam pre-pass and by fletcher_munson's two passes). */
+ * functions (scalars + block partials, ~128 KB).  rows, T > 0: the STFT-domain projections, which add two [rows, T]
+ * fp32 buffers (the staging buffer of an Adam pre-pass / of fletcher_munson's two passes, and in mode U the gradient
+ * summed over the parts). */
 size_t paa_scratch_bytes(const paa_handle* h, int rows, int T);
 /* Copies the PAA_S_* scalars of the last reducing call on `scratch` to the host (synchronises `stream`). */
 int paa_scalars(const paa_handle* h, const void* scratch, float* out8, void* stream);
