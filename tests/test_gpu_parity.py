@@ -170,6 +170,34 @@ def test_long_rows_interior_tiles(norm, sigma, T, env):
     close(paa.step_and_project(p.cuda(), grad.cuda(), clean.cuda(), args, env["it_gpu"], thr_g), want)
 
 
+@pytest.mark.parametrize("norm,sigma", [("max_phon", 0.03), ("min_max_freqs", 0.01), ("fletcher_munson", 0.1)])
+def test_long_rows_adam(norm, sigma, env):
+    """Adam + STFT-domain projection on rows with interior and row-end tiles: three steps through the drop-in
+    optimiser, perturbation and optimiser state against the oracle's torch.optim.Adam arithmetic."""
+    from paa_b200.training_utils import build
+    orc, paa = env["orc"], env["paa"]
+    T = 40000
+    g = torch.Generator().manual_seed(11)
+    clean = (torch.rand(2, T, generator=g) * 2 - 1) * 0.1
+    p = torch.randn(2, T, generator=g) * sigma
+    hp = orc.Hyper(norm_type=norm, optimizer_type="adam", lr=1e-3)
+    args = make_args(hp)
+    thr_c, thr_g = orc.phon_threshold(hp.n_fft, hp.sr, hp.max_phon_level), thr_gpu(args)
+    st = orc.AdamState(m=torch.zeros(2, T), v=torch.zeros(2, T))
+    pa = torch.nn.Parameter(p.clone().cuda())
+    opt, _ = build.create_optimizer(args, pa)
+    want = p.clone()
+    for step in range(3):
+        grad = torch.randn(2, T, generator=g)
+        want = orc.step_and_constrain(want, grad, clean, hp, env["it_cpu"], thr_c, adam=st)
+        with torch.no_grad():
+            pa.data = paa.step_and_project(pa.data, grad.cuda(), clean.cuda(), args, env["it_gpu"], thr_g, optimizer=opt)
+        close(pa.data, want)
+    close(opt.state[pa]["exp_avg"], st.m, 1e-6)
+    close(opt.state[pa]["exp_avg_sq"], st.v, 1e-6)
+    assert int(opt.state[pa]["step"]) == 3
+
+
 def test_fm_identity_roundtrip_option(env):
     orc, paa = env["orc"], env["paa"]
     g = torch.Generator().manual_seed(5)
