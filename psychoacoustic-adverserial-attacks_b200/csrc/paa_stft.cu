@@ -159,6 +159,22 @@ template <bool FAST>
 __device__ __forceinline__ float fm_term(const StftArgs& a, const float* __restrict__ tab, int F, int k, float re, float im) {
     // torch: power = abs(X)**2 (a square root and a square); FAST keeps re^2+im^2, one rounding away from it
     const float P = FAST ? fmaf(re, re, im * im) : [&] { const float m = sqrtf(fmaf(re, re, im * im)); return m * m; }();
+    if (FAST && a.fm_uniform) {
+        // Equally spaced phon knots (the reference's 0, 10, .., 90) in the fused kernel: branch free.  t = position of
+        // spl = 10 log10(P + 1e-10) on the knot axis in cells (one MUFU.LG2: abs error ~1e-6 dB, it only positions the
+        // query inside a 10 dB cell); cell index = round(t - 1/2) through the 1.5 * 2^23 magic constant (no F2I / I2F:
+        // at an exact knot either neighbouring cell interpolates to the same value, ties are harmless); out-of-range
+        // queries (and bins outside the frequency axis, whose table rows hold `fill`) take `fill`.
+        const float t = fmaf(__log2f(P + 1e-10f), 3.0102999566398120f * a.fm_inv_dk, -a.fm_k0 * a.fm_inv_dk);
+        const bool inr = !(t < 0.f) && !(t > (float)(a.fm_np - 1));
+        const float tc = inr ? t : 0.f;
+        const float tm = (tc - 0.5f) + 12582912.f;                 // 1.5 * 2^23: ulp 1, round to nearest even
+        const int i = min(__float_as_int(tm) & 0xff, a.fm_np - 2);  // 0 <= tc <= np-1  =>  0 <= i <= np-2 already
+        const float tp = tc - (tm - 12582912.f);
+        const float c0 = tab[64 + i * F + k], c1 = tab[64 + (i + 1) * F + k];
+        const float w = fmaf(tp, c1 - c0, c0);
+        return P * (inr ? w : a.fm_fill);
+    }
     // FAST: MUFU.LG2 (abs error ~1e-6 dB, it only positions the query inside a 10 dB cell)
     const float spl = FAST ? 3.0102999566398120f * __log2f(P + 1e-10f) : 10.f * log10f(P + 1e-10f);
     float w = a.fm_fill;
