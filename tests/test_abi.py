@@ -139,3 +139,24 @@ def test_host_tables_against_scipy_directly():
         want = (10.0 / al) * np.log10(a + (0.4 * 10.0 ** ((tf + lu) / 10.0 - 9.0)) ** al) - lu + 94.0
         assert np.abs(L.iso226_spl(phon, f) - want).max() < 1e-9
         assert np.abs(orc.iso226_spl(phon, f) - want).max() < 1e-9
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """struct paa_step / paa_parts as the C compiler lays them out against the ctypes mirrors in paa_lib.py."""
+    import ctypes
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    from paa_b200 import paa_lib as L
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "paa.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %d\\n", sizeof(paa_step), offsetof(paa_step, grad), '
+                   'offsetof(paa_step, adam_t), offsetof(paa_step, eps), offsetof(paa_step, parts), sizeof(paa_parts), '
+                   'offsetof(paa_parts, clean_stats), offsetof(paa_parts, clean_numel), PAA_MAX_PARTS); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [ctypes.sizeof(L.Step), L.Step.grad.offset, L.Step.adam_t.offset, L.Step.eps.offset, L.Step.parts.offset,
+            ctypes.sizeof(L.Parts), L.Parts.clean_stats.offset, L.Parts.clean_numel.offset, L.MAX_PARTS]
+    assert got == want
