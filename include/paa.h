@@ -62,9 +62,11 @@ enum { PAA_STEP_NONE = 0, PAA_STEP_PGD = 1, PAA_STEP_ADAM = 2 };
 typedef struct paa_parts {
     int           n;                            /* ranks, 1..PAA_MAX_PARTS                                        */
     const float*  grad[PAA_MAX_PARTS];          /* rank r's partial dL/dp [rows, T]; summed left to right in fp32  */
-    const double* clean_stats[PAA_MAX_PARTS];   /* rank r's {sum clean^2, sum |clean[t+1]-clean[t]|} (paa_clean_stats);
-                                                   NULL entries = statistics come from the `clean` argument        */
-    int64_t       clean_numel;                  /* numel of the whole clean batch (all ranks)                      */
+    const double* clean_stats[PAA_MAX_PARTS];   /* rank r's {sum clean^2, sum |clean[t+1]-clean[t]|, numel(clean)}
+                                                   (paa_clean_stats); NULL entries = statistics come from `clean`  */
+    int64_t       clean_numel;                  /* numel of the whole clean batch (all ranks); 0 = the kernels sum
+                                                   the parts' third statistic instead (uneven / changing shards:
+                                                   no host-side agreement on the batch size is needed)             */
 } paa_parts;
 
 typedef struct paa_step {
@@ -102,7 +104,7 @@ int paa_num_frames(const paa_handle* h, int T);       /* T' = 1 + T/hop (centre=
 /* Scratch a call needs.  rows = T = 0: the reducing time-domain projections (l2, snr, tv) and the paa_spec_fm_*
  * functions (scalars + block partials, ~128 KB).  rows, T > 0: the STFT-domain projections, which add two [rows, T]
  * fp32 buffers (the staging buffer of an Adam pre-pass / of fletcher_munson's two passes, and in mode U the gradient
- * summed over the parts). */
+ * summed over the parts) and fletcher_munson's per-tile partials. */
 size_t paa_scratch_bytes(const paa_handle* h, int rows, int T);
 /* Copies the PAA_S_* scalars of the last reducing call on `scratch` to the host (synchronises `stream`). */
 int paa_scalars(const paa_handle* h, const void* scratch, float* out8, void* stream);
@@ -132,10 +134,10 @@ int paa_project_tv(paa_handle* h, const float* p_in, float* p_out, int rows, int
                    const float* clean, int clean_rows, int clean_T, double tv_epsilon,
                    const paa_step* step, void* scratch, void* stream);                         /* projections.py:56-66 */
 
-/* Mode U helper: out2[0] = sum clean^2, out2[1] = sum over rows of sum_t |clean[r,t+1]-clean[r,t]| of this rank's
- * utterances (fp64 on the device, fixed summation order); goes into paa_parts.clean_stats.  Uses the partials area of
- * `scratch`. */
-int paa_clean_stats(paa_handle* h, const float* clean, int rows, int T, double* out2, void* scratch, void* stream);
+/* Mode U helper: out3[0] = sum clean^2, out3[1] = sum over rows of sum_t |clean[r,t+1]-clean[r,t]|, out3[2] = rows*T of
+ * this rank's utterances (fp64 on the device, fixed summation order); goes into paa_parts.clean_stats.  Uses the
+ * partials area of `scratch`. */
+int paa_clean_stats(paa_handle* h, const float* clean, int rows, int T, double* out3, void* scratch, void* stream);
 
 /* ---- step + projection, STFT domain (train.py:38-66): STFT -> per-bin op -> ISTFT in ONE kernel,
  * the spectrum never reaches HBM.  p_out must NOT alias p_in.  p_out is [rows, out_len]; samples
@@ -146,9 +148,13 @@ int paa_clean_stats(paa_handle* h, const float* clean, int rows, int T, double* 
  * max_phon: spl_thresh_F is the device array build.py:325-348 makes (F floats); the fused kernel clips in the
  * linear domain, |X'| = min(|X| + 1e-8, 10^(thr/20)), which equals the reference's dB round trip up to its own
  * fp32 rounding (~1e-6 relative); paa_spec_phon_level below performs the literal dB round trip.
- * fletcher_munson needs paa_set_fm_grid first (PAA_ERR_STATE otherwise) and is two passes: norm, then
- * exact_roundtrip != 0: ISTFT(scale * STFT(q)) as the reference computes it;
- * exact_roundtrip == 0: scale * q on the reconstructed span (the same thing algebraically, 8 B/sample). */
+ * fletcher_munson needs paa_set_fm_grid first (PAA_ERR_STATE otherwise) and is two passes: the weighted norm (one
+ * fp64 partial per tile in scratch -- sized by paa_scratch_bytes(rows, T), no limit on rows x tiles), then
+ * exact_roundtrip == 0 (what the Python drop-in passes by default): scale * q on the span the inverse transform
+ *   reconstructs, zeros behind it -- ISTFT(s * STFT(q)) = s * q there, 8 B/sample, and the kernel finalizes the norm
+ *   itself (two launches in all);
+ * exact_roundtrip != 0: the literal ISTFT(scale * STFT(q)) of the reference (finalize launch + a second transform;
+ *   differs from the identity form only by the round trip's own fp32 rounding, ~5e-7 relative). */
 int paa_project_min_max_freqs(paa_handle* h, const float* p_in, float* p_out, int rows, int T, int out_len,
                               double min_freq, double max_freq,
                               const paa_step* step, void* scratch, void* stream);              /* projections.py:68-80 */

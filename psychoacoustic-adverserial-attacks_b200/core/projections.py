@@ -26,6 +26,8 @@ def project_snr(clean, perturbation, snr_db, _step=None):
     """Rescale so that SNR(clean, perturbation) >= snr_db (projections.py:11-35; the target norm uses
     clean.numel() whatever the shape of the perturbation)."""
     L.need_cuda(clean, perturbation)
+    if _empty(perturbation):                         # mean of nothing is NaN: `snr >= snr_db` is False, the norm is 0 < 1e-8
+        return perturbation.detach().clone()
     p, c = L.f32c(perturbation.detach()), L.f32c(clean.detach())
     plan = L.plan_plain(p)
     rows, T = _rows(p)

@@ -103,7 +103,6 @@ int paa_create(int device, int n_fft, int hop, int sr, paa_handle** out) {
     std::memcpy(blob.data() + h->off_post, post.data(), post.size() * 4);
     e = cudaMalloc(&h->d_blob, h->blob_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_blob, blob.data(), h->blob_bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_thr_tmp, (size_t)h->F * 4);
     if (e != cudaSuccess) { int rc = paa_cuda_fail(h, e); paa_destroy(h); return rc; }
     *out = h;
     return PAA_OK;
@@ -112,7 +111,6 @@ int paa_create(int device, int n_fft, int hop, int sr, paa_handle** out) {
 int paa_destroy(paa_handle* h) {
     if (!h) return PAA_OK;
     cudaFree(h->d_blob);
-    cudaFree(h->d_thr_tmp);
     cudaFree(h->d_fm_blob);
     delete h;
     return PAA_OK;
@@ -126,7 +124,9 @@ size_t paa_scratch_bytes(const paa_handle* h, int rows, int T) {
     if (!h || rows < 0 || T < 0) return 0;
     // scalars + block partials always; the [rows, T] staging buffer only for the STFT-domain projections
     // (twice: mode U keeps the summed gradient of an STFT-domain projection behind the staging buffer)
-    return (size_t)kScalarBytes + kPartialBytes + 2 * (((size_t)rows * (size_t)T * sizeof(float) + 255) / 256 * 256) + 256;
+    // and one fp64 partial per fletcher_munson tile behind them
+    const size_t fm = (rows > 0 && T > 0) ? (scratch_fm_tiles(rows, T, h->hop) * sizeof(double) + 255) / 256 * 256 : 0;
+    return (size_t)kScalarBytes + kPartialBytes + 2 * (((size_t)rows * (size_t)T * sizeof(float) + 255) / 256 * 256) + fm + 256;
 }
 
 int paa_scalars(const paa_handle* h, const void* scratch, float* out8, void* stream) {

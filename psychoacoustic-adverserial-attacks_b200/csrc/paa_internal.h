@@ -5,7 +5,7 @@
 #include <vector>
 #include "../../include/paa.h"
 
-#define PAA_VERSION 101
+#define PAA_VERSION 200
 
 // Host tables of one (n_fft, hop, sr) plan, mirrored on the device.
 struct paa_handle {
@@ -33,7 +33,6 @@ struct paa_handle {
     float fm_fill = 1.f;
     int fm_uniform = 0;              // knots equally spaced -> direct cell lookup
     float fm_k0 = 0.f, fm_klast = 0.f, fm_inv_dk = 0.f;
-    float* d_thr_tmp = nullptr;      // [F] scaled phon threshold for the un-fused spectrum op
 };
 
 // ---- status helpers -------------------------------------------------------------------------
@@ -79,6 +78,16 @@ static inline float* scratch_stage(void* s) { return (float*)((char*)s + kScalar
 static inline float* scratch_gsum(void* s, int rows, int T) {
     const size_t stage = ((size_t)rows * (size_t)T * sizeof(float) + 255) / 256 * 256;
     return (float*)((char*)s + kScalarBytes + kPartialBytes + stage);
+}
+
+// fletcher_munson pass A: one fp64 partial per tile, behind the two [rows, T] buffers (no cap on rows x tiles)
+static inline size_t scratch_fm_tiles(int rows, int T, int hop) {
+    const size_t frames = 1 + (size_t)T / (size_t)(hop > 0 ? hop : 1);
+    return (size_t)rows * ((frames + 15) / 16 + 1);            // a tile holds >= 16 frames
+}
+static inline double* scratch_fm_partials(void* s, int rows, int T) {
+    const size_t stage = ((size_t)rows * (size_t)T * sizeof(float) + 255) / 256 * 256;
+    return (double*)((char*)s + kScalarBytes + kPartialBytes + 2 * stage);
 }
 
 // ---- step parameters as the kernels see them -------------------------------------------------

@@ -832,38 +832,65 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
         if (tid == 0) {
             double s = 0.0;
             for (int w = 0; w < kWarps; ++w) s += (double)red[w];
-            a.partials[2 * (size_t)blockIdx.x] = s;
-            a.partials[2 * (size_t)blockIdx.x + 1] = 0.0;
+            a.partials[blockIdx.x] = s;                  // stride 1: scratch_fm_partials, one slot per tile
         }
     }
 }
 
 // ---- fletcher_munson finalize: norm = sqrt(sum), scale = norm <= eps ? 1 : eps / max(norm, 1e-8) ---
-__global__ void k_fm_finalize(const double* partials, int nblocks, float* scalars, float fm_eps, int apply) {
+// projections.py:130-132.  torch's clamp(min=1e-8) propagates NaN (a NaN norm makes the whole output NaN); fmaxf
+// would not, so the NaN case is kept explicit.
+__device__ __forceinline__ void fm_final(double tot, float fm_eps, int apply, float& scale, float& norm) {
+    norm = sqrtf((float)tot);
+    scale = 1.f;
+    if (apply && !(norm <= fm_eps)) {
+        const float floor_n = (norm != norm) ? norm : fmaxf(norm, 1e-8f);
+        scale = __frcp_rn(floor_n) * fm_eps;
+    }
+}
+// Fixed-order sum of `n` block partials (stride `stride` doubles) by one CTA; every CTA that runs it gets the same bits.
+__device__ __forceinline__ double fm_sum_partials(const double* partials, int n, int stride) {
     __shared__ double sh[32];
+    __shared__ double s_tot;
     double s = 0.0;
-    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) s += partials[2 * i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[(size_t)i * stride];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
         double tot = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sh[w];
-        const float norm = sqrtf((float)tot);
-        float scale = 1.f;
-        if (apply && !(norm <= fm_eps)) scale = __frcp_rn(fmaxf(norm, 1e-8f)) * fm_eps;   // projections.py:130-132
-        scalars[PAA_S_SCALE] = scale;
-        scalars[PAA_S_NORM] = norm;
-        scalars[PAA_S_AUX0] = (float)tot;
-        scalars[PAA_S_AUX1] = 0.f;
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) tot += sh[w];
+        s_tot = tot;
+    }
+    __syncthreads();
+    return s_tot;
+}
+__device__ __forceinline__ void fm_store_scalars(float* scalars, float scale, float norm, double tot) {
+    scalars[PAA_S_SCALE] = scale;
+    scalars[PAA_S_NORM] = norm;
+    scalars[PAA_S_AUX0] = (float)tot;
+    scalars[PAA_S_AUX1] = 0.f;
+}
+__global__ void k_fm_finalize(const double* partials, int nblocks, int stride, float* scalars, float fm_eps, int apply) {
+    const double tot = fm_sum_partials(partials, nblocks, stride);
+    if (threadIdx.x == 0) {
+        float scale, norm;
+        fm_final(tot, fm_eps, apply, scale, norm);
+        fm_store_scalars(scalars, scale, norm, tot);
     }
 }
 
-// p_out[row, n] = scale * q[row, n] for n < valid, 0 up to out_len:  ISTFT(s * STFT(q)) = s * q on the
-// samples the inverse reconstructs (used when the caller waives the exact round trip).
-__global__ void k_fm_scale_identity(const float* __restrict__ q, float* __restrict__ out, int rows, int T, int out_len,
-                                    int valid, const float* __restrict__ scalars) {
-    const float sc = scalars[PAA_S_SCALE];
+// Pass B of fletcher_munson in its default form.  ISTFT(s * STFT(q)) = s * q on the samples the inverse
+// reconstructs, so:  p_out[row, n] = scale * q[row, n] for n < valid, 0 up to out_len.  The kernel finalizes the norm
+// itself: every CTA re-sums pass A's tile partials in the same fixed order (as k_fused does behind its grid
+// barrier), so no finalize launch sits between the two passes; CTA 0 publishes the scalars.
+__global__ void __launch_bounds__(256) k_fm_scale_identity(const float* __restrict__ q, float* __restrict__ out, int rows, int T,
+                                                          int out_len, int valid, const double* __restrict__ partials,
+                                                          int nparts, float fm_eps, float* __restrict__ scalars) {
+    const double tot = fm_sum_partials(partials, nparts, 1);
+    float sc, norm;
+    fm_final(tot, fm_eps, 1, sc, norm);
+    if (blockIdx.x == 0 && threadIdx.x == 0) fm_store_scalars(scalars, sc, norm, tot);
     const int lim = min(valid, T);
     const bool vec = (T % 4 == 0) && (out_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
@@ -879,7 +906,7 @@ __global__ void k_fm_scale_identity(const float* __restrict__ q, float* __restri
         const float* src = q + (size_t)r * T + c;
         float* dst = out + (size_t)r * out_len + c;
         if (vec && c + 3 < lim) {
-            float4 v = *reinterpret_cast<const float4*>(src);
+            float4 v = __ldcs(reinterpret_cast<const float4*>(src));
             v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
             *reinterpret_cast<float4*>(dst) = v;
         } else {
@@ -894,7 +921,22 @@ __global__ void k_fm_scale_identity(const float* __restrict__ q, float* __restri
 
 // ---- element-wise spectrum kernels for the un-fused public functions -------------------------------
 template <int OP>
-__global__ void k_spec_op(StftArgs a, int F, const float* thr_scaled) {
+__global__ void k_spec_op(StftArgs a, int F) {
+    // OP_PHON_DB: thr[k] = spl_thresh[k] - max(spl_thresh) + reference_db, rebuilt by every CTA in shared memory
+    // (F <= 513 floats): no temporary that concurrent streams would share
+    __shared__ float s_thr[OP == OP_PHON_DB ? 520 : 1];
+    __shared__ float s_red[32];
+    if (OP == OP_PHON_DB) {
+        float mx = -INFINITY;
+        for (int k = threadIdx.x; k < F; k += blockDim.x) mx = fmaxf(mx, a.spl_thresh[k]);
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+        __syncthreads();
+        mx = s_red[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, s_red[w]);
+        for (int k = threadIdx.x; k < F; k += blockDim.x) s_thr[k] = (a.spl_thresh[k] - mx) + a.ref_db;
+        __syncthreads();
+    }
     const long long n = (long long)a.rows * F * a.n_frames;
     const float scale = OP == OP_SCALE ? a.scalars[PAA_S_SCALE] : 1.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -904,20 +946,9 @@ __global__ void k_spec_op(StftArgs a, int F, const float* thr_scaled) {
         else { t = (int)(i % a.n_frames); k = (int)((i / a.n_frames) % F); b = (int)(i / ((long long)F * a.n_frames)); }
         const long long off = b * a.sb + k * a.sf + t * a.st;
         float2 X = a.spec_in[off];
-        apply_op<OP, false>(a, thr_scaled, scale, 1.f, k, X.x, X.y);
+        apply_op<OP, false>(a, s_thr, scale, 1.f, k, X.x, X.y);
         a.spec_out[off] = X;
     }
-}
-__global__ void k_thr_scaled(const float* spl, int F, float ref_db, float* out) {
-    __shared__ float sh[32];
-    float mx = -INFINITY;
-    for (int k = threadIdx.x; k < F; k += blockDim.x) mx = fmaxf(mx, spl[k]);
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    mx = sh[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, sh[w]);
-    for (int k = threadIdx.x; k < F; k += blockDim.x) out[k] = (spl[k] - mx) + ref_db;
 }
 __global__ void k_spec_fm_partials(StftArgs a, int F) {
     const long long n = (long long)a.rows * F * a.n_frames;
@@ -959,8 +990,14 @@ template <int NFFT, int SRC, int SINK, int OP>
 int launch(paa_handle* h, StftArgs& a, int grid, cudaStream_t st) {
     size_t smem = smem_bytes<NFFT>(h, SRC, SINK, OP, a.frames_per_tile, a.blocks_per_tile);
     auto kern = k_stft<NFFT, SRC, SINK, OP>;
-    // per launch: the attribute belongs to the (function, device) pair and a process may hold handles on several devices
-    PAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the attribute belongs to the (function, device) pair: raised once per pair (and again only if another handle
+    // geometry needs more), not on every launch -- small shapes are launch-latency bound
+    static int granted[64];
+    const int dev = h->device & 63;
+    if ((size_t)__atomic_load_n(&granted[dev], __ATOMIC_ACQUIRE) < smem) {
+        PAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        __atomic_store_n(&granted[dev], (int)smem, __ATOMIC_RELEASE);
+    }
     kern<<<grid, kThreadsStft, smem, st>>>(a);
     PAA_LAUNCH_CHECK(h);
     return PAA_OK;
@@ -1140,24 +1177,25 @@ int paa_project_fletcher_munson(paa_handle* h, const float* p_in, float* p_out, 
     a.q_out = grad ? scratch_stage(scratch) : nullptr;
     a.vec_ok = aligned16(src) && (T % 4 == 0) && (!grad || aligned16(grad));
     a.tiles_per_row = (n_frames + a.frames_per_tile - 1) / a.frames_per_tile;
-    a.partials = scratch_partials(scratch);
+    a.partials = scratch_fm_partials(scratch, rows, T);        // one slot per tile, sized by paa_scratch_bytes(rows, T)
     const int grid = rows * a.tiles_per_row;
-    if (grid > kMaxPartialBlocks) return PAA_ERR_SHAPE;
     rc = launch_n<SRC_TIME, SINK_REDUCE, OP_NONE>(h, a, grid, st);
     if (rc) return rc;
     float* scalars = scratch_scalars(scratch);
-    k_fm_finalize<<<1, 256, 0, st>>>(a.partials, grid, scalars, (float)fm_epsilon, 1);
-    PAA_LAUNCH_CHECK(h);
-    // pass B: ISTFT(scale * STFT(q)).  q is the stepped signal (staging buffer) or the input itself.
+    // pass B.  q is the stepped signal (staging buffer) or the input itself.
     const float* q = grad ? scratch_stage(scratch) : src;
     if (exact_roundtrip) {
+        // the reference's literal ISTFT(scale * STFT(q)): finalize launch + a second fused transform
+        k_fm_finalize<<<1, 256, 0, st>>>(a.partials, grid, 1, scalars, (float)fm_epsilon, 1);
+        PAA_LAUNCH_CHECK(h);
         StftArgs b{};
         b.scalars = scalars;
         return run_fused<OP_SCALE>(h, b, q, nullptr, 0.f, p_out, rows, T, out_len, st);
     }
     const long long n = (long long)rows * ((out_len + 3) / 4);
     const int g2 = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8);
-    k_fm_scale_identity<<<std::max(g2, 1), 256, 0, st>>>(q, p_out, rows, T, out_len, h->hop * (n_frames - 1), scalars);
+    k_fm_scale_identity<<<std::max(g2, 1), 256, 0, st>>>(q, p_out, rows, T, out_len, h->hop * (n_frames - 1), a.partials, grid,
+                                                       (float)fm_epsilon, scalars);
     PAA_LAUNCH_CHECK(h);
     return PAA_OK;
 }
@@ -1206,7 +1244,7 @@ int paa_spec_min_max_freqs(paa_handle* h, const float* spec_in, float* spec_out,
     a.spec_in = reinterpret_cast<const float2*>(spec_in); a.spec_out = reinterpret_cast<float2*>(spec_out);
     a.sb = sb; a.sf = sf; a.st = stt;
     set_band(h, a, min_freq, max_freq);
-    k_spec_op<OP_MASK><<<spec_grid(h, (long long)rows * h->F * n_frames), 256, 0, (cudaStream_t)stream>>>(a, h->F, nullptr);
+    k_spec_op<OP_MASK><<<spec_grid(h, (long long)rows * h->F * n_frames), 256, 0, (cudaStream_t)stream>>>(a, h->F);
     PAA_LAUNCH_CHECK(h);
     return PAA_OK;
 }
@@ -1221,9 +1259,8 @@ int paa_spec_phon_level(paa_handle* h, const float* spec_in, float* spec_out, in
     a.spec_in = reinterpret_cast<const float2*>(spec_in); a.spec_out = reinterpret_cast<float2*>(spec_out);
     a.sb = sb; a.sf = sf; a.st = stt;
     cudaStream_t st = (cudaStream_t)stream;
-    k_thr_scaled<<<1, 256, 0, st>>>(spl_thresh_F, h->F, (float)phon_reference_db, h->d_thr_tmp);
-    PAA_LAUNCH_CHECK(h);
-    k_spec_op<OP_PHON_DB><<<spec_grid(h, (long long)rows * h->F * n_frames), 256, 0, st>>>(a, h->F, h->d_thr_tmp);
+    a.spl_thresh = spl_thresh_F; a.ref_db = (float)phon_reference_db;
+    k_spec_op<OP_PHON_DB><<<spec_grid(h, (long long)rows * h->F * n_frames), 256, 0, st>>>(a, h->F);
     PAA_LAUNCH_CHECK(h);
     return PAA_OK;
 }
@@ -1243,10 +1280,10 @@ static int spec_fm(paa_handle* h, const float* spec_in, float* spec_out, int row
     const int grid = std::min(spec_grid(h, n), kMaxPartialBlocks);
     k_spec_fm_partials<<<grid, 256, 0, st>>>(a, h->F);
     PAA_LAUNCH_CHECK(h);
-    k_fm_finalize<<<1, 256, 0, st>>>(a.partials, grid, scratch_scalars(scratch), (float)fm_epsilon, apply);
+    k_fm_finalize<<<1, 256, 0, st>>>(a.partials, grid, 2, scratch_scalars(scratch), (float)fm_epsilon, apply);
     PAA_LAUNCH_CHECK(h);
     if (apply) {
-        k_spec_op<OP_SCALE><<<spec_grid(h, n), 256, 0, st>>>(a, h->F, nullptr);
+        k_spec_op<OP_SCALE><<<spec_grid(h, n), 256, 0, st>>>(a, h->F);
         PAA_LAUNCH_CHECK(h);
     }
     return PAA_OK;

@@ -289,6 +289,7 @@ struct FinalArgs {
     // mode U: the clean-audio sum (snr: index 0, tv: index 1) is the sum of the per-rank statistics, index order
     const double* cstat[PAA_MAX_PARTS];
     int ncstat, cstat_idx;
+    int numel_from_stats;   // mode U with paa_parts.clean_numel == 0: numel(clean) = sum of the parts' third statistic
 };
 __device__ __forceinline__ double clean_total(const FinalArgs& a, double local) {
     if (a.ncstat == 0) return local;
@@ -299,22 +300,33 @@ __device__ __forceinline__ double clean_total(const FinalArgs& a, double local) 
     return t;
 }
 
+// numel of the whole clean batch: a host constant, or (mode U, uneven shards) the sum of the per-rank counts
+__device__ __forceinline__ double clean_numel(const FinalArgs& a) {
+    if (!a.numel_from_stats) return a.n_clean;
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < PAA_MAX_PARTS; ++k)
+        if (k < a.ncstat) t += a.cstat[k][2];
+    return t;
+}
+
 // The reference's data-dependent branch, in its fp32 arithmetic, from the two global sums.
 template <int NORM>
 __device__ __forceinline__ void final_math(double tot0, double tot1, const FinalArgs& a, float& scale, float& norm,
                                            float& aux0, float& aux1) {
     scale = 1.f; norm = 0.f; aux0 = 0.f; aux1 = 0.f;
+    const double n_clean = NORM == NORM_SNR ? clean_numel(a) : 1.0;
     if (NORM == NORM_L2) {                                   // projections.py:41-46
         norm = sqrtf((float)tot0);
         if (norm > a.eps) scale = __frcp_rn(norm) * a.eps;     // python `eps / tensor` = reciprocal()*eps
     } else if (NORM == NORM_SNR) {                           // projections.py:11-35
         const float p_noise = (float)(tot0 / a.n_p);
-        const float p_sig = (float)(tot1 / a.n_clean);
+        const float p_sig = (float)(tot1 / n_clean);
         aux0 = p_sig;
         aux1 = 10.f * log10f(p_sig / (p_noise + 1e-12f));
         norm = sqrtf((float)tot0);
         if (!(aux1 >= a.eps) && !(norm < 1e-8f)) {
-            const float want = sqrtf((p_sig / (float)a.snr_linear) * (float)a.n_clean);
+            const float want = sqrtf((p_sig / (float)a.snr_linear) * (float)n_clean);
             scale = want / norm;
         }
     } else {                                                 // projections.py:56-66
@@ -574,13 +586,13 @@ __global__ void __launch_bounds__(kThreads) k_clean_stats(const float* __restric
     double wide[2] = {(double)e, (double)tv};
     block_sum<2>(wide, partials + 2 * (int64_t)blockIdx.x);
 }
-__global__ void __launch_bounds__(kThreads) k_clean_stats_final(const double* partials, int nblocks, double* out2) {
+__global__ void __launch_bounds__(kThreads) k_clean_stats_final(const double* partials, int nblocks, double* out3, double numel) {
     double acc[2] = {0.0, 0.0};
     for (int i = threadIdx.x; i < nblocks; i += kThreads) { acc[0] += partials[2 * i]; acc[1] += partials[2 * i + 1]; }
     __shared__ double tot[2];
     block_sum<2>(acc, tot);
     __syncthreads();
-    if (threadIdx.x == 0) { out2[0] = tot[0]; out2[1] = tot[1]; }
+    if (threadIdx.x == 0) { out3[0] = tot[0]; out3[1] = tot[1]; out3[2] = numel; }
 }
 // out = sum of the gradient parts (for the STFT-domain projections, whose tiles re-read halo samples)
 __global__ void __launch_bounds__(kThreads) k_sum_parts(StepDev s, float* out, int64_t n, bool vec) {
@@ -716,6 +728,29 @@ int launch_reduce(paa_handle* h, const ReduceArgs& a, const StepDev& sd, int gri
     return PAA_OK;
 }
 
+// The cooperative kernel of one (NORM, STEP): its dynamic shared-memory ceiling is raised and its co-residency queried
+// once per device (not per call: small shapes are launch-latency bound), the answers cached per instantiation.
+constexpr int kMaxDevices = 64;
+template <int NORM, int STEP>
+cudaError_t fused_kernel(const paa_handle* h, void** kern, int* blocks_per_sm) {
+    static int cached[kMaxDevices];          // 0 = unknown, else 1 + blocks per SM
+    void* k = (void*)k_fused<NORM, STEP>;
+    *kern = k;
+    const int dev = h->device & (kMaxDevices - 1);
+    int c = __atomic_load_n(&cached[dev], __ATOMIC_ACQUIRE);
+    if (c == 0) {
+        const size_t smem_max = (size_t)kSCMax * kFT * sizeof(float4);
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        int bps = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, kFT, smem_max);
+        if (e != cudaSuccess) return e;
+        c = 1 + bps;
+        __atomic_store_n(&cached[dev], c, __ATOMIC_RELEASE);
+    }
+    *blocks_per_sm = c - 1;
+    return cudaSuccess;
+}
+
 template <int NORM>
 int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int T, const float* clean,
                    int64_t clean_n, int clean_T, float eps, double snr_linear, const paa_step* step, void* scratch,
@@ -726,9 +761,9 @@ int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int
     const paa_parts* parts = step ? step->parts : nullptr;
     const bool stats = NORM != NORM_L2 && parts && parts->n > 0 && parts->clean_stats[0];
     if (stats) {
-        if (parts->n > PAA_MAX_PARTS || parts->clean_numel <= 0) return PAA_ERR_SHAPE;
+        if (parts->n > PAA_MAX_PARTS || parts->clean_numel < 0) return PAA_ERR_SHAPE;
         for (int k = 0; k < parts->n; ++k) if (!parts->clean_stats[k]) return PAA_ERR_NULL;
-        clean = nullptr; clean_n = parts->clean_numel; clean_T = 1;
+        clean = nullptr; clean_n = std::max<int64_t>(parts->clean_numel, 1); clean_T = 1;
     }
     if (NORM != NORM_L2 && !clean && !stats) return PAA_ERR_NEED_CLEAN;
     if (NORM != NORM_L2 && (clean_n <= 0 || clean_T <= 0)) return PAA_ERR_SHAPE;
@@ -762,33 +797,41 @@ int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int
     f.eps = eps; f.snr_linear = snr_linear; f.n_p = (double)n; f.n_clean = (double)clean_n;
     if (stats) {
         f.ncstat = parts->n; f.cstat_idx = NORM == NORM_SNR ? 0 : 1;
+        f.numel_from_stats = parts->clean_numel == 0;
         for (int k = 0; k < parts->n; ++k) f.cstat[k] = parts->clean_stats[k];
     }
     if (vec && !h->no_coop) {
         // single cooperative launch; fall through to the three-kernel form only if the device refuses it
         void* kern = nullptr;
+        int bps = 0;
+        cudaError_t e = cudaSuccess;
         switch (step_code(mode, sd)) {
-            case PAA_STEP_NONE: kern = (void*)k_fused<NORM, PAA_STEP_NONE>; break;
-            case PAA_STEP_PGD: kern = (void*)k_fused<NORM, PAA_STEP_PGD>; break;
-            case PAA_STEP_ADAM: kern = (void*)k_fused<NORM, PAA_STEP_ADAM>; break;
-            case PAA_STEP_PGD | kStepParts: kern = (void*)k_fused<NORM, PAA_STEP_PGD | kStepParts>; break;
-            default: kern = (void*)k_fused<NORM, PAA_STEP_ADAM | kStepParts>; break;
+            case PAA_STEP_NONE: e = fused_kernel<NORM, PAA_STEP_NONE>(h, &kern, &bps); break;
+            case PAA_STEP_PGD: e = fused_kernel<NORM, PAA_STEP_PGD>(h, &kern, &bps); break;
+            case PAA_STEP_ADAM: e = fused_kernel<NORM, PAA_STEP_ADAM>(h, &kern, &bps); break;
+            case PAA_STEP_PGD | kStepParts: e = fused_kernel<NORM, PAA_STEP_PGD | kStepParts>(h, &kern, &bps); break;
+            default: e = fused_kernel<NORM, PAA_STEP_ADAM | kStepParts>(h, &kern, &bps); break;
         }
-        const int max_grid = 2 * h->num_sms;
-        const int64_t work4 = (work + 3) / 4;
-        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, (work4 + kFT - 1) / kFT));
-        const int64_t iters = ((n >> 2) + (int64_t)grid * kFT - 1) / ((int64_t)grid * kFT);
-        int sc_iters = (int)std::max<int64_t>(0, std::min<int64_t>(kSCMax, iters - (mode == PAA_STEP_ADAM ? 2 : kRC)));
-        size_t smem = (size_t)sc_iters * kFT * sizeof(float4);
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSCMax * kFT * sizeof(float4)));
-        f.nblocks = grid;
-        void* params[] = {(void*)&a, (void*)&sd, (void*)&f, (void*)&sc_iters};
-        if (e == cudaSuccess) e = cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kFT), params, smem, st);
-        if (e == cudaSuccess) {
-            __atomic_add_fetch(&g_paa_launches, 1, __ATOMIC_RELAXED);
-            return PAA_OK;
+        if (e != cudaSuccess) return paa_cuda_fail(h, e);
+        if (bps > 0) {
+            const int max_grid = bps * h->num_sms;              // co-residency as the occupancy calculator reports it
+            const int64_t work4 = (work + 3) / 4;
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, (work4 + kFT - 1) / kFT));
+            const int64_t iters = ((n >> 2) + (int64_t)grid * kFT - 1) / ((int64_t)grid * kFT);
+            int sc_iters = (int)std::max<int64_t>(0, std::min<int64_t>(kSCMax, iters - (mode == PAA_STEP_ADAM ? 2 : kRC)));
+            size_t smem = (size_t)sc_iters * kFT * sizeof(float4);
+            f.nblocks = grid;
+            void* params[] = {(void*)&a, (void*)&sd, (void*)&f, (void*)&sc_iters};
+            e = cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kFT), params, smem, st);
+            if (e == cudaSuccess) {
+                __atomic_add_fetch(&g_paa_launches, 1, __ATOMIC_RELAXED);
+                return PAA_OK;
+            }
+            (void)cudaGetLastError();
+            // only "this device / configuration cannot launch cooperatively" selects the three-kernel form for good
+            if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorNotSupported) return paa_cuda_fail(h, e);
         }
-        (void)cudaGetLastError();
+        h->last_cuda_error = (int)e;
         h->no_coop = 1;
     }
     int grid = std::min(grid_for(h, vec ? (work + 3) / 4 : work), kMaxPartialBlocks);
@@ -868,16 +911,16 @@ int paa_launch_sum_parts(paa_handle* h, const StepDev& sd, float* out, int64_t n
 
 extern "C" {
 
-int paa_clean_stats(paa_handle* h, const float* clean, int rows, int T, double* out2, void* scratch, void* stream) {
+int paa_clean_stats(paa_handle* h, const float* clean, int rows, int T, double* out3, void* scratch, void* stream) {
     PaaDeviceGuard device_guard(h);
-    if (!h || !clean || !out2 || !scratch) return PAA_ERR_NULL;
+    if (!h || !clean || !out3 || !scratch) return PAA_ERR_NULL;
     if (rows <= 0 || T <= 0) return PAA_ERR_SHAPE;
     const int64_t n = (int64_t)rows * T;
     const int grid = std::min(grid_for(h, n), kMaxPartialBlocks);
     cudaStream_t st = (cudaStream_t)stream;
     k_clean_stats<<<grid, kThreads, 0, st>>>(clean, n, T, scratch_partials(scratch));
     PAA_LAUNCH_CHECK(h);
-    k_clean_stats_final<<<1, kThreads, 0, st>>>(scratch_partials(scratch), grid, out2);
+    k_clean_stats_final<<<1, kThreads, 0, st>>>(scratch_partials(scratch), grid, out3, (double)n);
     PAA_LAUNCH_CHECK(h);
     return PAA_OK;
 }

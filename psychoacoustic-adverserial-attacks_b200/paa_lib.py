@@ -177,7 +177,8 @@ class Plan:
         check(lib.paa_create(device.index, self.n_fft, self.hop, self.sr, C.byref(h)))
         self.h = h
         self._scratch: Optional[torch.Tensor] = None
-        self._fm_key = None
+        self._fm_obj = None              # the installed interpolator itself: a live reference, so its id cannot be reused
+        self._fm_sig = None
 
     def __del__(self):
         try:
@@ -198,15 +199,18 @@ class Plan:
         return np.array(out[:], dtype=np.float32)
 
     def set_fm_grid(self, interp) -> None:
-        """Install interp.grid / interp.values (the object iso.py:238-266 returns) once per object."""
-        key = id(interp)
-        if key == self._fm_key:
+        """Install interp.grid / interp.values (the object iso.py:238-266 returns).  The same object is installed
+        once; a different object is compared by content (300 doubles) and re-installed only if it differs."""
+        if interp is self._fm_obj:
             return
         g0, g1 = (np.ascontiguousarray(g, dtype=np.float64) for g in interp.grid)
         v = np.ascontiguousarray(interp.values, dtype=np.float64)
         fill = 1.0 if getattr(interp, "fill_value", 1.0) is None else float(interp.fill_value)
-        check(lib.paa_set_fm_grid(self.h, _dptr(g0), g0.size, _dptr(g1), g1.size, _dptr(v), fill), self.h)
-        self._fm_key = key
+        sig = (g0.tobytes(), g1.tobytes(), v.tobytes(), fill)
+        if sig != self._fm_sig:
+            check(lib.paa_set_fm_grid(self.h, _dptr(g0), g0.size, _dptr(g1), g1.size, _dptr(v), fill), self.h)
+            self._fm_sig = sig
+        self._fm_obj = interp
 
 
 _plans: Dict[Tuple[int, int, int, int], Plan] = {}

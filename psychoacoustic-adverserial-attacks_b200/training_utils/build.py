@@ -62,16 +62,24 @@ class PerturbationAdam(torch.optim.Adam):
         raise KeyError("parameter is not managed by this optimizer")
 
     def fused_step_descriptor(self, p, grad):
-        """Advance the step counter and describe this update for the C ABI (struct paa_step)."""
+        """Describe the NEXT update (step count state['step'] + 1) for the C ABI (struct paa_step).  The counter itself
+        advances in ``commit_step`` once the launch that consumed the descriptor has been accepted, so a call that
+        raises (bad shape, CUDA error) leaves the optimiser state where it was."""
         key = next(q for g in self.param_groups for q in g["params"] if q.data_ptr() == p.data_ptr() or q is p)
         g = self._group_of(key)
         if g["weight_decay"] != 0 or g["amsgrad"] or g["maximize"]:
             raise NotImplementedError("PerturbationAdam supports the reference's configuration only "
                                       "(no weight decay / amsgrad / maximize)")
         st = self._state_for(key)
-        st["step"] += 1
-        return L.make_step(L.STEP_ADAM, grad, g["lr"], st["exp_avg"], st["exp_avg_sq"], int(st["step"].item()),
+        desc = L.make_step(L.STEP_ADAM, grad, g["lr"], st["exp_avg"], st["exp_avg_sq"], int(st["step"].item()) + 1,
                            g["betas"], g["eps"])
+        desc._adam_state = st
+        return desc
+
+    @staticmethod
+    def commit_step(desc):
+        """The update described by ``desc`` was enqueued: state['step'] += 1 (torch/optim/adam.py:457)."""
+        desc._adam_state["step"] += 1
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -89,6 +97,7 @@ class PerturbationAdam(torch.optim.Adam):
                 rows, T = p.numel() // p.shape[-1], p.shape[-1]
                 L.check(L.lib.paa_step_only(plan.h, p.data_ptr(), p.data_ptr(), rows, T, L.step_ref(desc),
                                             L.stream_ptr(p.device)), plan.h)
+                self.commit_step(desc)
         return loss
 
 

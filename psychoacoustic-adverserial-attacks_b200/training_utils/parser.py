@@ -30,8 +30,13 @@ def create_arg_parser():
     p.add_argument("--win_length", type=int, default=1024)
     p.add_argument("--seed", type=int, default=5)
     p.add_argument("--device", type=str, default="cuda")
-    # not in the reference: waive the bit-faithful STFT->scale->ISTFT second pass of fletcher_munson
-    p.add_argument("--fm_identity_roundtrip", action="store_true")
+    # not in the reference: fletcher_munson's second pass as the literal ISTFT(scale * STFT(q)) of projections.py:116-133
+    # instead of the algebraically identical scale * q on the reconstructed span (the default, ~5e-7 apart)
+    p.add_argument("--fm_exact_roundtrip", action="store_true")
+    # not in the reference: run the model call of train.py:136-145 in chunks of this many utterances (0 = whole batch).
+    # The CTC reduction is "sum", so chunk losses and chunk gradients add up to the whole-batch ones; the step and the
+    # projection always see the whole batch.
+    p.add_argument("--micro_batch", type=int, default=0)
     # not in the reference: x_adv = clamp(clean + p) and its backward as libpaa kernels instead of autograd's passes
     p.add_argument("--fused_compose", action="store_true")
     # not in the reference: keep loss / greedy ids on the device and decode them after the epoch (no per-step host sync)

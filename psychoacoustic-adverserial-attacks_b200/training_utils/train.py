@@ -62,7 +62,9 @@ def _frequency_domain(p, clean_audio, args, interp, spl_thresh, step):
                                         float(args.phon_reference_db), L.step_ref(step), scratch, stream)
     elif kind == "fletcher_munson":
         plan.set_fm_grid(interp)
-        exact = 0 if getattr(args, "fm_identity_roundtrip", False) else 1
+        # pass B defaults to the identity form s*q (ISTFT(s*STFT(q)) = s*q on the reconstructed span, ~5e-7 from the
+        # literal round trip); --fm_exact_roundtrip asks for the reference's second transform
+        exact = 1 if getattr(args, "fm_exact_roundtrip", False) else 0
         rc = L.lib.paa_project_fletcher_munson(plan.h, x.data_ptr(), out.data_ptr(), rows, T, out_len,
                                                float(args.fm_epsilon), exact, L.step_ref(step), scratch, stream)
     else:
@@ -122,9 +124,33 @@ def step_and_project(p, grad, clean_audio, args, interp, spl_thresh, optimizer: 
                 raise ValueError("Adam optimizer selected but optimizer is None")
             step = optimizer.fused_step_descriptor(p, g)
             L.attach_parts(step, parts)
+            out = _dispatch(p, clean_audio, args, interp, spl_thresh, step)
+            optimizer.commit_step(step)               # only after the launch was accepted
+            return out
         else:
             raise NotImplementedError(f"Optimization type not implemented: {args.optimizer_type!r}")
         return _dispatch(p, clean_audio, args, interp, spl_thresh, step)
+
+
+def _chunked_forward_backward(model, clean_audio, p, target_texts, processor, args, micro, sign, loss_helpers):
+    """train.py:136-145 + the backward of :158 / :170 over chunks of ``micro`` utterances.  Returns the whole-batch loss
+    (sum of the chunk losses, detached) and the concatenated logits; p.grad holds the whole-batch gradient."""
+    B = clean_audio.shape[0]
+    per_row = p.shape[0] == B and B > 1
+    total, logit_chunks = None, []
+    for lo in range(0, B, micro):
+        hi = min(lo + micro, B)
+        pc = p[lo:hi] if per_row else p
+        if getattr(args, "fused_compose", False):
+            perturbed = compose.compose_clamp(clean_audio[lo:hi], pc)
+        else:
+            perturbed = (clean_audio[lo:hi] + pc).clamp_(-1.0, 1.0)
+        loss_c, logits_c = loss_helpers.get_loss_for_training(model=model, data=perturbed, target_texts=target_texts[lo:hi],
+                                                              processor=processor, args=args)
+        (sign * loss_c).backward()
+        total = loss_c.detach() if total is None else total + loss_c.detach()
+        logit_chunks.append(logits_c.detach())
+    return total, torch.cat(logit_chunks, dim=0)
 
 
 def train_epoch(args, train_data_loader, p, model, epoch, processor, interp, wer_metric, spl_thresh, optimizer):
@@ -148,12 +174,26 @@ def train_epoch(args, train_data_loader, p, model, epoch, processor, interp, wer
         p.requires_grad_(True)
         if p.grad is not None:
             p.grad = None
-        if getattr(args, "fused_compose", False):          # one kernel forward, one backward (core/compose.py)
-            perturbed = compose.compose_clamp(clean_audio, p)
+        micro = int(getattr(args, "micro_batch", 0) or 0)
+        chunked = 0 < micro < clean_audio.shape[0]
+        if chunked:
+            # the gradient source in chunks: forward + backward per chunk, p.grad accumulates the
+            # chunk gradients (CTC reduction "sum": they add up to the whole-batch gradient); the step + projection
+            # below sees the whole batch once
+            if args.optimizer_type == "adam":
+                if optimizer is None:
+                    raise ValueError("Adam optimizer selected but optimizer is None")
+                optimizer.zero_grad(set_to_none=True)
+            sign = direction if args.optimizer_type == "pgd" else -1 * direction
+            loss, logits = _chunked_forward_backward(model, clean_audio, p, target_texts, processor, args, micro, sign,
+                                                     loss_helpers)
         else:
-            perturbed = (clean_audio + p).clamp_(-1.0, 1.0)
-        loss, logits = loss_helpers.get_loss_for_training(model=model, data=perturbed, target_texts=target_texts,
-                                                          processor=processor, args=args)
+            if getattr(args, "fused_compose", False):          # one kernel forward, one backward (core/compose.py)
+                perturbed = compose.compose_clamp(clean_audio, p)
+            else:
+                perturbed = (clean_audio + p).clamp_(-1.0, 1.0)
+            loss, logits = loss_helpers.get_loss_for_training(model=model, data=perturbed, target_texts=target_texts,
+                                                              processor=processor, args=args)
         if defer:
             # keep the loss and the greedy ids on the device; one synchronisation at the end of the epoch
             pending.append((loss.detach(), logits.detach().argmax(-1), target_texts))
@@ -166,14 +206,16 @@ def train_epoch(args, train_data_loader, p, model, epoch, processor, interp, wer
 
         exchange = getattr(args, "universal_exchange", None)      # mode U: one perturbation shared by all ranks
         if args.optimizer_type == "pgd":
-            (direction * loss).backward()
+            if not chunked:
+                (direction * loss).backward()
             parts = exchange.publish(p.grad, clean_audio, args.norm_type) if exchange is not None else None
             p = step_and_project(p, p.grad, clean_audio, args, interp, spl_thresh, parts=parts).detach()
         elif args.optimizer_type == "adam":
             if optimizer is None:
                 raise ValueError("Adam optimizer selected but optimizer is None")
-            optimizer.zero_grad(set_to_none=True)
-            (-1 * direction * loss).backward()
+            if not chunked:
+                optimizer.zero_grad(set_to_none=True)
+                (-1 * direction * loss).backward()
             parts = exchange.publish(p.grad, clean_audio, args.norm_type) if exchange is not None else None
             with torch.no_grad():
                 p.data = step_and_project(p.data, p.grad, clean_audio, args, interp, spl_thresh, optimizer=optimizer,

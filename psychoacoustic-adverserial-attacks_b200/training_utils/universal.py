@@ -28,7 +28,7 @@ except ImportError:
 
 
 def reduce_partials(grad: torch.Tensor, stats: torch.Tensor, group=None):
-    """Baseline exchange: in-place all-reduce(sum) of the partial gradient and of the (2,) fp64 clean statistics.
+    """Baseline exchange: in-place all-reduce(sum) of the partial gradient and of the (3,) fp64 clean statistics.
     Device agnostic (NCCL on GPUs, gloo in the CPU tests)."""
     dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
@@ -55,9 +55,8 @@ class UniversalExchange:
         self.rows, self.T, self.device, self.backend = int(rows), int(T), device, backend
         self.n = self.rows * self.T
         self.n_al = (self.n + 3) // 4 * 4                       # statistics start 16-byte aligned
-        self.slot = self.n_al + 4                                # [gradient | 2 doubles]
+        self.slot = self.n_al + 8                                # [gradient | 3 doubles: sum x^2, sum |dx|, numel | pad]
         self.step = 0
-        self._numel_cache = {}
         self._keep = None
         if backend == "auto":
             # peer-memory exchange when the box supports it (NVLink P2P + symmetric memory), else the NCCL baseline.
@@ -89,17 +88,11 @@ class UniversalExchange:
         self.ptrs = [int(x) for x in self.hdl.buffer_ptrs]
         self.buf.zero_()
 
-    def _global_numel(self, clean: torch.Tensor) -> int:
-        key = tuple(clean.shape)
-        if key not in self._numel_cache:                          # one tiny all-reduce per batch shape
-            t = torch.tensor([clean.numel()], dtype=torch.int64, device=clean.device)
-            dist.all_reduce(t, group=self.group)
-            self._numel_cache[key] = int(t.item())
-        return self._numel_cache[key]
-
     def publish(self, grad: Optional[torch.Tensor], clean: Optional[torch.Tensor], norm_type: Optional[str] = None):
         """Make this rank's partial gradient and clean statistics visible to all ranks for this step.
-        Everything is enqueued on the current stream; no host synchronisation after the first call per shape.
+        Everything is enqueued on the current stream, no host synchronisation and no host-side agreement between the
+        ranks: the size of the whole clean batch (project_snr's ``clean.numel()``) travels as a third statistic next to
+        the two sums and is added up on the device, so shards may be uneven and change from step to step.
         ``norm_type``: when given, the clean statistics are computed only for the norms that use them (snr, tv)."""
         if norm_type is not None and norm_type not in ("snr", "tv"):
             clean = None
@@ -120,16 +113,15 @@ class UniversalExchange:
             stats_ptr = self.buf.data_ptr() + (off + self.n_al) * 4
             L.check(L.lib.paa_clean_stats(plan.h, c2.data_ptr(), c2.shape[0], c2.shape[1], stats_ptr, plan.scratch(0, 0),
                                           L.stream_ptr(c.device)), plan.h)
-            clean_numel = self._global_numel(c)
         if self.backend == "symmetric":
             self.hdl.barrier(channel=slot)                          # device side, on the current stream
             gp = [p + off * 4 for p in self.ptrs] if grad is not None else None
             sp = [p + (off + self.n_al) * 4 for p in self.ptrs] if have_stats else None
         else:
-            stats = self.buf[off + self.n_al:off + self.n_al + 4].view(torch.float64)
+            stats = self.buf[off + self.n_al:off + self.n_al + 6].view(torch.float64)
             reduce_partials(gview, stats, self.group)
             gp = [gview.data_ptr()] if grad is not None else None
             sp = [stats.data_ptr()] if have_stats else None
         if gp is None and sp is None:
             return None
-        return L.make_parts(gp, sp, clean_numel)
+        return L.make_parts(gp, sp, clean_numel)          # clean_numel = 0: the kernels sum the parts' third statistic

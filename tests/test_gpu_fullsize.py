@@ -1,0 +1,131 @@
+"""Parity at BASELINE.json's full shapes.  The CPU oracle would need minutes per case at these sizes, so the oracle's
+torch arithmetic (oracle/paa_oracle.py -- the pinned restatement of the reference, bit-identical to it on the golden
+fixtures) is executed on CUDA tensors on the same GPU and compared with libpaa element by element:
+
+    snr 32 x 10 s | max_phon, fletcher_munson 64 x 15 s | tv, min_max_freqs 128 x 10 s | l2 512 x 10 s | linf 4 x 5 s, 128 x 10 s
+
+for one perturbation row per utterance (rows = B) AND the reference's universal (1, T) perturbation (rows = 1), for the
+PGD step AND two Adam steps (optimiser state compared too).  Bars: max|a-b|/max|b| <= 1e-5 and ||a-b||/||b|| <= 1e-5.
+One mid-size shape per norm stays compared with the oracle on the CPU (test_gpu_parity.py)."""
+import pytest
+import torch
+
+from conftest import rel_l2, rel_max
+from test_gpu_parity import make_args, thr_gpu
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+SR = 16000
+
+SHAPES = [
+    # norm, B, seconds, sigma  (sigma chosen so that the constraint binds)
+    ("linf", 4, 5, 1e-3), ("linf", 128, 10, 1e-3), ("snr", 32, 10, 0.01), ("max_phon", 64, 15, 0.03),
+    ("fletcher_munson", 64, 15, 0.1), ("tv", 128, 10, 0.01), ("min_max_freqs", 128, 10, 0.01), ("l2", 512, 10, 0.01),
+]
+
+
+def _inputs(B, T, rows, sigma, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    clean = (torch.rand(B, T, generator=g, device="cuda") * 2 - 1) * 0.1
+    p = torch.randn(rows, T, generator=g, device="cuda") * sigma
+    grad = torch.randn(rows, T, generator=g, device="cuda")
+    grad[torch.rand(rows, T, generator=g, device="cuda") < 0.01] = 0.0          # sign(0) = 0
+    return clean, p, grad
+
+
+def _check(got, want, what):
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    d = (got.double() - want.double())
+    a = float(d.abs().max() / want.double().abs().max().clamp_min(1e-300))
+    b = float(d.norm() / want.double().norm().clamp_min(1e-300))
+    assert a <= TOL and b <= TOL, (what, a, b)
+    return a, b
+
+
+@pytest.mark.parametrize("universal", [False, True], ids=["rowsB", "rows1"])
+@pytest.mark.parametrize("norm,B,sec,sigma", SHAPES)
+def test_baseline_shapes_pgd(norm, B, sec, sigma, universal):
+    import paa_b200
+    from oracle import paa_oracle as orc
+    from paa_b200.core import iso
+    T = sec * SR
+    rows = 1 if universal else B
+    clean, p, grad = _inputs(B, T, rows, sigma, 1234)
+    hp = orc.Hyper(norm_type=norm, optimizer_type="pgd", snr_db=40.0, device="cuda")
+    args = make_args(hp)
+    thr = thr_gpu(args)
+    it_cpu, it_gpu = orc.build_weight_interpolator(), iso.build_weight_interpolator()
+    want = orc.step_and_constrain(p, grad, clean, hp, it_cpu, thr)
+    got = paa_b200.step_and_project(p, grad, clean, args, it_gpu, thr)
+    _check(got, want, (norm, B, sec, rows, "pgd"))
+    # the projection alone (init_perturbation's call, build.py:303)
+    want = orc.constrain(p, clean, hp, it_cpu, thr)
+    got = paa_b200.perturbation_constraint(p, clean, args, it_gpu, thr)
+    _check(got, want, (norm, B, sec, rows, "proj"))
+
+
+@pytest.mark.parametrize("universal", [False, True], ids=["rowsB", "rows1"])
+@pytest.mark.parametrize("norm,B,sec,sigma", SHAPES)
+def test_baseline_shapes_adam(norm, B, sec, sigma, universal):
+    import paa_b200
+    from oracle import paa_oracle as orc
+    from paa_b200.core import iso
+    from paa_b200.training_utils import build
+    if norm == "fletcher_munson" and not universal:
+        steps = 1                      # the oracle's host interpolation of 30.8 M bins takes seconds per step
+    else:
+        steps = 2
+    T = sec * SR
+    rows = 1 if universal else B
+    clean, p, grad = _inputs(B, T, rows, sigma, 4321)
+    hp = orc.Hyper(norm_type=norm, optimizer_type="adam", snr_db=40.0, lr=1e-3, device="cuda")
+    args = make_args(hp)
+    thr = thr_gpu(args)
+    it_cpu, it_gpu = orc.build_weight_interpolator(), iso.build_weight_interpolator()
+    st = orc.AdamState(m=torch.zeros_like(p), v=torch.zeros_like(p))
+    pa = torch.nn.Parameter(p.clone())
+    opt, _ = build.create_optimizer(args, pa)
+    want = p
+    for s in range(steps):
+        gr = grad * (1.0 if s == 0 else -0.5)
+        want = orc.step_and_constrain(want, gr, clean, hp, it_cpu, thr, adam=st)
+        with torch.no_grad():
+            pa.data = paa_b200.step_and_project(pa.data, gr, clean, args, it_gpu, thr, optimizer=opt)
+        _check(pa.data, want, (norm, B, sec, rows, "adam", s))
+    _check(opt.state[pa]["exp_avg"], st.m, (norm, "exp_avg"))
+    _check(opt.state[pa]["exp_avg_sq"], st.v, (norm, "exp_avg_sq"))
+    assert int(opt.state[pa]["step"]) == steps
+
+
+def test_fletcher_munson_per_utterance_512x10s():
+    """10 240 tiles: more than the 8 192 block partials the other norms use -- the fletcher_munson partial area is sized
+    by the call, so no shape is refused.  Checked against the torch ops on the GPU with the weights of a small
+    random subset of rows recomputed... the whole tensor would cost the oracle's host interpolation 30 s, so the
+    comparison uses the scalar the reference computes (the weighted norm) and the linearity of the projection."""
+    import paa_b200
+    from oracle import paa_oracle as orc
+    from paa_b200 import paa_lib as L
+    from paa_b200.core import iso
+    B, T = 512, 160000
+    g = torch.Generator(device="cuda").manual_seed(9)
+    p = torch.randn(B, T, generator=g, device="cuda") * 0.1
+    clean = torch.zeros(1, T, device="cuda")
+    hp = orc.Hyper(norm_type="fletcher_munson", device="cuda")
+    args = make_args(hp)
+    it_gpu = iso.build_weight_interpolator()
+    out = paa_b200.perturbation_constraint(p, clean, args, it_gpu, None)
+    s = L.plan_for(p, args).scalars()
+    assert out.shape == p.shape and 0.0 < s[L.S_SCALE] < 1.0
+    # the weighted norm is additive over rows in the squared domain: compare with the sum of 8 chunks of 64 rows
+    tot = 0.0
+    for lo in range(0, B, 64):
+        paa_b200.perturbation_constraint(p[lo:lo + 64], clean, args, it_gpu, None)
+        tot += float(L.plan_for(p, args).scalars()[L.S_NORM]) ** 2
+    assert abs(tot ** 0.5 / float(s[L.S_NORM]) - 1) < 1e-5
+    # and one chunk against the oracle's torch arithmetic directly
+    want = orc.fm_weighted_norm(orc.stft(p[:16], hp.n_fft, hp.hop_length), orc.build_weight_interpolator(), hp.n_fft, hp.sr)
+    paa_b200.perturbation_constraint(p[:16], clean, args, it_gpu, None)
+    assert abs(float(L.plan_for(p, args).scalars()[L.S_NORM]) / float(want) - 1) < 1e-5
+    valid = 256 * (T // 256)
+    assert rel_max(out[:, :valid], p[:, :valid] * float(s[L.S_SCALE])) < 1e-5
+    assert float(out[:, valid:].abs().max()) == 0.0 if valid < T else True

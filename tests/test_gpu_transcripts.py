@@ -88,3 +88,116 @@ def test_transcripts_and_wer_identical(norm, opt):
         if opt == "pgd" and norm in ("linf", "l2", "snr", "tv"):   # an STFT-domain projection smears one flipped sample over n_fft
             assert float((d > tol).float().mean()) < frac_ok, f"step {step}: {float((d > tol).float().mean()):.4f} of samples differ"
         assert float((p_new - p_ref).norm() / p_ref.norm()) < 2e-2
+
+
+# ---- the real model: Wav2Vec2ForCTC(Wav2Vec2Config()) = wav2vec2-base, random init, at BASELINE.json's configs ----
+# oracle/transcript_check.py runs the reference arithmetic and libpaa side by side (teacher-forced: same p, same
+# gradient every step; free-running: each on its own trajectory) and reports every logit frame whose greedy token
+# differs, with the reference's top-1 minus top-2 margin on that frame.
+MARGIN = 1e-3      # logits are O(1); a frame whose two best tokens are closer than this is a numerical tie
+
+
+def base_model(dev):
+    from transformers import Wav2Vec2Config, Wav2Vec2ForCTC
+    torch.manual_seed(0)
+    m = Wav2Vec2ForCTC(Wav2Vec2Config()).eval().to(dev)
+    for q in m.parameters():
+        q.requires_grad_(False)
+    return m
+
+
+def _identity_case(norm, B, sec, rows, opt, mode, steps, micro=0, **over):
+    from oracle import paa_oracle as orc, transcript_check as tc
+    from paa_b200.core import iso
+    from paa_b200.training_utils import build, parser
+    dev = torch.device("cuda:0")
+    model = base_model(dev)
+    T = sec * 16000
+    g = torch.Generator().manual_seed(1234)
+    clean = ((torch.rand(B, T, generator=g) * 2 - 1) * 0.1).to(dev)
+    p0 = (torch.randn(rows, T, generator=g) * 0.01).to(dev)
+    kw = dict(norm_type=norm, optimizer_type=opt, attack_mode=mode, lr=1e-4, snr_db=40.0)
+    kw.update(over)
+    hp = orc.Hyper(device=str(dev), **kw)
+    args = parser.create_arg_parser().parse_args([])
+    for k, v in kw.items():
+        setattr(args, k, v)
+    args.device = str(dev)
+    thr = build.init_phon_threshold_tensor(args)
+    rep = tc.run(model, clean, ["hello world this is a test"] * B, args, hp, steps, p0, orc.build_weight_interpolator(),
+                 iso.build_weight_interpolator(), thr, micro=micro)
+    print(rep)
+    return rep, tc
+
+
+@pytest.mark.parametrize("rows", [1, 32], ids=["universal", "per_utterance"])
+def test_wav2vec2_base_configs1_snr_transcripts_identical(rows):
+    """BASELINE.json configs[1]: targeted 'delete' x5, snr 40 dB, PGD, batch 32 x 10 s, 20 steps."""
+    rep, tc = _identity_case("snr", 32, 10, rows, "pgd", "targeted", 20)
+    tf, fr = rep["teacher_forced"], rep["free_running"]
+    assert rep["max_rel_err_p_teacher_forced"] <= 1e-5
+    assert not tc.flips_above(tf, MARGIN), tf
+    assert tf["frames"] == 20 * 32 * 499
+    if tf["flips"] == 0:
+        assert tf["transcript_mismatch_steps"] == 0 and tf["wer_mismatch_steps"] == 0
+    assert not tc.flips_above(fr, MARGIN), fr
+    if fr["flips"] == 0:
+        assert fr["transcript_mismatch_steps"] == 0 and fr["wer_mismatch_steps"] == 0
+
+
+@pytest.mark.parametrize("norm,over", [("max_phon", {}), ("fletcher_munson", dict(fm_epsilon=2.0))])
+def test_wav2vec2_base_configs2_stft_transcripts_identical(norm, over):
+    """BASELINE.json configs[2]: untargeted STFT-domain projection, n_fft 1024, batch 64 x 15 s (universal p, the model
+    call in chunks of 32), 20 steps (fletcher_munson: 6 -- the oracle's host interpolation dominates)."""
+    steps = 20 if norm == "max_phon" else 6
+    rep, tc = _identity_case(norm, 64, 15, 1, "pgd", "untargeted", steps, micro=32, **over)
+    tf, fr = rep["teacher_forced"], rep["free_running"]
+    assert rep["max_rel_err_p_teacher_forced"] <= 1e-5
+    assert not tc.flips_above(tf, MARGIN), tf
+    if tf["flips"] == 0:
+        assert tf["transcript_mismatch_steps"] == 0 and tf["wer_mismatch_steps"] == 0
+    assert not tc.flips_above(fr, MARGIN), fr
+
+
+def test_wav2vec2_base_adam_l2_transcripts_identical():
+    """Adam (the reference's default optimiser) + l2 on wav2vec2-base, 16 x 10 s, universal p, 10 steps."""
+    rep, tc = _identity_case("l2", 16, 10, 1, "adam", "untargeted", 10, l2_size=0.5, lr=1e-3)
+    tf = rep["teacher_forced"]
+    assert rep["max_rel_err_p_teacher_forced"] <= 1e-5
+    assert not tc.flips_above(tf, MARGIN), tf
+    if tf["flips"] == 0:
+        assert tf["transcript_mismatch_steps"] == 0 and tf["wer_mismatch_steps"] == 0
+
+
+def test_micro_batched_gradient_source_matches_whole_batch():
+    """train_epoch with --micro_batch (the model call of train.py:136-145 in chunks, CTC reduction "sum") against the
+    whole-batch call: same loss, same transcripts, and a gradient that differs only by summation order."""
+    import paa_b200  # noqa: F401
+    from paa_b200.core import loss_helpers
+    from paa_b200.training_utils import parser, train
+    dev = torch.device("cuda:0")
+    model = small_model(dev)
+    g = torch.Generator().manual_seed(8)
+    B, T = 8, 16000
+    loader = [(((torch.rand(B, T, generator=g) * 2 - 1) * 0.1), ["hello world this is a test"] * B) for _ in range(2)]
+    for rows in (1, B):
+        for opt in ("pgd", "adam"):
+            from paa_b200.training_utils import build
+            res = {}
+            for micro in (0, 3):
+                args = parser.create_arg_parser().parse_args(["--norm_type", "l2", "--optimizer_type", opt, "--lr", "1e-3",
+                                                              "--l2_size", "0.5", "--micro_batch", str(micro)])
+                args.device = str(dev)
+                p0 = (torch.randn(rows, T, generator=torch.Generator().manual_seed(2)) * 1e-3).to(dev)
+                optimizer = None
+                if opt == "adam":
+                    p0 = torch.nn.Parameter(p0)
+                    optimizer, _ = build.create_optimizer(args, p0)
+                wer = loss_helpers.WerMetric()
+                r = train.train_epoch(args, loader, p0, model, 0, None, None, wer, None, optimizer)
+                res[micro] = (r.p.detach().clone(), r.avg_ctc, r.avg_wer, wer.errors, wer.words)
+            a, b = res[0], res[3]
+            assert abs(a[1] - b[1]) <= 1e-5 * abs(a[1]) and a[2:] == b[2:]
+            # sign(g) of near-zero gradient elements may differ with the summation order; everything else is equal
+            differ = ((a[0] - b[0]).abs() > 1e-6 * a[0].abs().max()).float().mean()
+            assert float(differ) < (5e-3 if opt == "pgd" else 5e-2), (rows, opt, float(differ))

@@ -9,7 +9,8 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-NORMS = [("linf", 1e-3), ("l2", 0.01), ("snr", 0.01), ("tv", 0.01), ("max_phon", 0.03), ("min_max_freqs", 0.01)]
+NORMS = [("linf", 1e-3), ("l2", 0.01), ("snr", 0.01), ("tv", 0.01), ("max_phon", 0.03), ("min_max_freqs", 0.01),
+         ("fletcher_munson", 0.1)]
 B, T, STEPS = 4, 8192, 3
 
 
@@ -54,8 +55,10 @@ def _worker(rank, world, port, backend, optimizer, out):
             outs = []
             for step in range(STEPS):
                 clean, grads = _inputs(step)
-                lo = rank * (B // world)
-                clean_r = clean[lo:lo + B // world].to(dev)
+                # uneven shards that change from step to step (3+1, 1+3, 3+1): the size of the whole batch is summed on
+                # the device from the ranks' statistics, no host-side agreement
+                cut = 3 if step % 2 == 0 else 1
+                clean_r = (clean[:cut] if rank == 0 else clean[cut:]).to(dev)
                 parts = exch.publish(grads[rank].to(dev), clean_r, norm)
                 with torch.no_grad():
                     q = paa_b200.step_and_project(p.data if opt else p, grads[rank].to(dev), clean_r, args, interp, thr,
@@ -177,3 +180,72 @@ def test_universal_train_epoch_reproduces_the_single_process_epoch(norm):
     # gradient is ~0 may take the other sign (a PGD step of 2*lr apart); everything else must agree.
     differ = ((pu - p1).abs() > 1e-6 * p1.abs().max()).float().mean()
     assert float(differ) < 5e-3, float(differ)
+
+
+# ---- the same kernels on ONE GPU: paa_parts whose buffers are all local ------------------------------------------
+# struct paa_parts only holds device pointers; nothing requires them to be peer memory.  Passing 2, 3 and 8 local
+# partial-gradient buffers and per-part clean statistics exercises every kStepParts instantiation (k_step_clamp,
+# k_fused, k_reduce), k_sum_parts + staging for the STFT-domain projections, and the device-side sum of the clean
+# statistics (incl. the batch size), against the oracle's step on the summed gradient and the whole batch.
+@pytest.mark.parametrize("optimizer", ["pgd", "adam"])
+@pytest.mark.parametrize("G", [2, 3, 8])
+@pytest.mark.parametrize("norm,sigma", NORMS)
+def test_local_parts_match_oracle_on_summed_gradient(norm, sigma, G, optimizer):
+    import paa_b200
+    from conftest import rel_l2, rel_max
+    from oracle import paa_oracle as orc
+    from paa_b200 import paa_lib as L
+    from paa_b200.core import iso
+    from paa_b200.training_utils import build, parser
+
+    dev = torch.device("cuda:0")
+    Tl, Bl = 20000, 9
+    g = torch.Generator().manual_seed(100 * G + len(norm))
+    args = parser.create_arg_parser().parse_args(["--norm_type", norm, "--optimizer_type", optimizer, "--snr_db", "40",
+                                                  "--lr", "1e-4"])
+    args.device = str(dev)
+    hp = orc.Hyper(norm_type=norm, optimizer_type=optimizer, snr_db=40.0, lr=1e-4)
+    it_cpu, it_gpu = orc.build_weight_interpolator(), iso.build_weight_interpolator()
+    thr_c, thr_g = orc.phon_threshold(hp.n_fft, hp.sr, hp.max_phon_level), build.init_phon_threshold_tensor(args)
+    p_ref = torch.randn(1, Tl, generator=g) * sigma
+    p_new = p_ref.clone().to(dev)
+    opt = None
+    if optimizer == "adam":
+        p_new = p_new.requires_grad_(True)
+        opt, _ = build.create_optimizer(args, p_new)
+    adam = orc.AdamState(m=torch.zeros(1, Tl), v=torch.zeros(1, Tl)) if optimizer == "adam" else None
+    plan = L.plan_plain(p_new)
+    for step in range(2):
+        clean = (torch.rand(Bl, Tl, generator=g) * 2 - 1) * 0.1
+        grads = torch.randn(G, 1, Tl, generator=g)
+        grads[:, :, ::89] = 0.0
+        total = grads[0].clone()
+        for k in range(1, G):
+            total = total + grads[k]                            # left to right in fp32: what the kernels add
+        p_ref = orc.step_and_constrain(p_ref, total, clean, hp, it_cpu, thr_c, adam=adam)
+        # uneven row shards of the clean batch: the first parts take one row each, the last one the rest
+        bounds = list(range(G)) + [Bl] if G < Bl else list(range(Bl)) + [Bl]
+        shards = [clean[bounds[k]:bounds[k + 1]] for k in range(len(bounds) - 1)]
+        while len(shards) < G:                                    # more parts than rows: empty-statistics parts
+            shards.append(None)
+        g_dev = [grads[k].to(dev).contiguous() for k in range(G)]
+        stats = torch.zeros(G, 4, dtype=torch.float64, device=dev)
+        keep = []
+        for k, sh in enumerate(shards):
+            if sh is None:
+                continue
+            c = sh.to(dev).contiguous()
+            keep.append(c)
+            L.check(L.lib.paa_clean_stats(plan.h, c.data_ptr(), c.shape[0], c.shape[1], stats[k].data_ptr(),
+                                          plan.scratch(0, 0), L.stream_ptr(dev)), plan.h)
+        parts = L.make_parts([t.data_ptr() for t in g_dev], [stats[k].data_ptr() for k in range(G)], 0)
+        clean_local = keep[0]                                     # a rank only holds its own shard
+        with torch.no_grad():
+            q = paa_b200.step_and_project(p_new.data if opt else p_new, g_dev[0], clean_local, args, it_gpu, thr_g,
+                                          optimizer=opt, parts=parts)
+        if opt:
+            p_new.data = q
+        else:
+            p_new = q
+        a, b = rel_max(q.cpu(), p_ref), rel_l2(q.cpu(), p_ref)
+        assert a <= 1e-5 and b <= 1e-5, (norm, G, optimizer, step, a, b)
