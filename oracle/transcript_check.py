@@ -17,8 +17,20 @@ Two comparisons per step k:
                   2*lr on a small fraction of samples; the transcripts are compared all the same.
 
 A *flip* is a logit frame whose argmax differs; its *margin* is the reference's top-1 minus top-2 logit on that frame
-(how decisive the frame was).  A random-init wav2vec2 has nearly flat logits, so near-ties exist; the report carries
-every flip with the smallest and largest margin seen, and the caller asserts "no flip above margin M".
+(how decisive the frame was).  A random-init wav2vec2 has nearly flat logits (std ~0.5, top-2 margins down to 1e-7), so
+near-ties exist; the report carries every flip with the smallest and largest margin seen, and the caller asserts "no
+flip above margin M".
+
+What sets M is the gradient source, not the hot path: torch runs cuDNN convolutions in TF32 by default
+(torch.backends.cudnn.allow_tf32 = True, the setting the reference inherits), and TF32 rounds the convolution inputs to
+10 mantissa bits -- a last-bit fp32 difference in one waveform sample that crosses a TF32 rounding boundary becomes a
+5e-4 RELATIVE change of that sample, and the logits move by ~1e-3.  Two controls make that visible:
+
+  control_one_ulp   the reference's own p_{k+1} with a random half of its samples moved to the adjacent fp32 value (what
+                    any other correct fp32 implementation -- another torch version, another reduction order -- could
+                    produce) against the unmodified one: same flip statistics as libpaa's.
+  cudnn_tf32=False  the same comparison with the gradient source in full fp32: the logit differences fall to the 1e-6
+                    range and the flips with them.
 """
 from __future__ import annotations
 
@@ -76,10 +88,30 @@ def _blank():
             "transcript_mismatch_steps": 0, "wer_mismatch_steps": 0, "wer_last": None}
 
 
+def one_ulp_nudge(p: torch.Tensor, seed: int) -> torch.Tensor:
+    """A random half of the samples moved to the adjacent fp32 value (direction random)."""
+    g = torch.Generator(device=p.device).manual_seed(seed)
+    r = torch.rand(p.shape, generator=g, device=p.device)
+    up = torch.nextafter(p, torch.full_like(p, float("inf")))
+    dn = torch.nextafter(p, torch.full_like(p, float("-inf")))
+    return torch.where(r < 0.25, up, torch.where(r < 0.5, dn, p))
+
+
 def run(model, clean: torch.Tensor, texts, args, hp, steps: int, p0: torch.Tensor, interp_cpu=None, interp_gpu=None,
-        spl_thresh=None, micro: int = 0, free_running: bool = True) -> Dict:
+        spl_thresh=None, micro: int = 0, free_running: bool = True, control: bool = True,
+        cudnn_tf32: Optional[bool] = None) -> Dict:
     """`args` drives libpaa (paa_b200.step_and_project), `hp` the oracle; both describe the same attack.
-    PGD and Adam are supported (Adam keeps one state per trajectory)."""
+    PGD and Adam are supported (Adam keeps one state per trajectory).  `cudnn_tf32`: None = torch's default (True)."""
+    prev_tf32 = torch.backends.cudnn.allow_tf32
+    if cudnn_tf32 is not None:
+        torch.backends.cudnn.allow_tf32 = bool(cudnn_tf32)
+    try:
+        return _run(model, clean, texts, args, hp, steps, p0, interp_cpu, interp_gpu, spl_thresh, micro, free_running, control)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev_tf32
+
+
+def _run(model, clean, texts, args, hp, steps, p0, interp_cpu, interp_gpu, spl_thresh, micro, free_running, control) -> Dict:
     import paa_b200
     from paa_b200.training_utils import build as pbuild
 
@@ -99,8 +131,9 @@ def run(model, clean: torch.Tensor, texts, args, hp, steps: int, p0: torch.Tenso
     pa_free = torch.nn.Parameter(p_free.clone()) if adam else None
     opt_free = pbuild.create_optimizer(args, pa_free)[0] if adam else None
 
-    tf, fr = _blank(), _blank()
+    tf, fr, ctl = _blank(), _blank(), _blank()
     max_rel_p = 0.0
+    same_input_diff = 0.0
     for k in range(steps):
         _, _, g_ref = _forward(model, clean, p_ref, labels, micro, True, sign)
         with torch.no_grad():
@@ -116,6 +149,12 @@ def run(model, clean: torch.Tensor, texts, args, hp, steps: int, p0: torch.Tenso
         _, lg_ref, _ = _forward(model, clean, p_ref, labels, micro, False, sign)
         _, lg_tf, _ = _forward(model, clean, p_tf, labels, micro, False, sign)
         _compare(lg_ref, lg_tf, tf, texts if hp.attack_mode == "untargeted" else label_texts)
+        if control:
+            _, lg_ctl, _ = _forward(model, clean, one_ulp_nudge(p_ref, 1000 + k), labels, micro, False, sign)
+            _compare(lg_ref, lg_ctl, ctl, texts if hp.attack_mode == "untargeted" else label_texts)
+            if k == 0:          # is the forward pass itself deterministic on identical input?
+                _, lg_again, _ = _forward(model, clean, p_ref, labels, micro, False, sign)
+                same_input_diff = float((lg_again - lg_ref).abs().max())
         if free_running:
             cur = pa_free.data if adam else p_free
             _, _, g_free = _forward(model, clean, cur, labels, micro, True, sign)
@@ -128,8 +167,11 @@ def run(model, clean: torch.Tensor, texts, args, hp, steps: int, p0: torch.Tenso
             _, lg_free, _ = _forward(model, clean, nxt, labels, micro, False, sign)
             _compare(lg_ref, lg_free, fr, texts if hp.attack_mode == "untargeted" else label_texts)
     out = {"steps": steps, "batch": int(clean.shape[0]), "p_rows": int(p0.shape[0]), "norm_type": hp.norm_type,
-           "optimizer": hp.optimizer_type, "max_rel_err_p_teacher_forced": float(f"{max_rel_p:.3e}"),
-           "teacher_forced": tf}
+           "optimizer": hp.optimizer_type, "cudnn_tf32": bool(torch.backends.cudnn.allow_tf32),
+           "max_rel_err_p_teacher_forced": float(f"{max_rel_p:.3e}"), "teacher_forced": tf}
+    if control:
+        ctl["same_input_logit_diff"] = same_input_diff
+        out["control_one_ulp"] = ctl
     if free_running:
         p_last = pa_free.data if adam else p_free
         fr["rel_l2_p_vs_reference"] = float(f"{float((p_last - p_ref).norm() / p_ref.norm()):.3e}")

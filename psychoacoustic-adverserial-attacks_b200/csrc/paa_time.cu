@@ -94,16 +94,13 @@ __device__ __forceinline__ float stepped1(const float* p, int64_t i, const StepD
 
 // The same in two halves, so that the loads of the next float4 can be issued before the arithmetic on the
 // current one (software pipelining in k_fused: memory-level parallelism, not instruction count, bounds it).
-struct Raw4 { float4 p, g, m, v; float np, ng; };      // np/ng: the element after the float4 (tv, last lane only)
+// np/ng: the element after the float4 (tv, last lane only); c/nc: the clean audio at the same index (snr, tv)
+struct Raw4 { float4 p, g, m, v; float np, ng; float4 c; float nc; };
 template <int STEP>
-__device__ __forceinline__ Raw4 load_raw4(const float* p, int64_t i, const StepDev& s) {
-    Raw4 r;
+__device__ __forceinline__ void load_raw4(Raw4& r, const float* p, int64_t i, const StepDev& s) {
     r.p = ld4(p + i);
-    r.g = r.m = r.v = make_float4(0.f, 0.f, 0.f, 0.f);
-    r.np = r.ng = 0.f;
     if ((STEP & 3) != PAA_STEP_NONE) r.g = ldg4<STEP>(s, i);
     if ((STEP & 3) == PAA_STEP_ADAM) { r.m = ld4(s.m + i); r.v = ld4(s.v + i); }
-    return r;
 }
 template <int STEP, bool WRITE_STATE>
 __device__ __forceinline__ float4 finish4(Raw4 r, int64_t i, const StepDev& s) {
@@ -416,6 +413,30 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     int colp = 0, stepp = 0;
     if (NORM == NORM_TV) { colp = (int)((tid * 4) % a.T); stepp = (int)((nth * 4) % a.T); }
 
+    // The clean audio (snr: sum of squares, tv: total variation) rides the same loop as the perturbation: float4 i4 of
+    // p, grad (Adam: m, v) and clean are requested together, so every thread keeps three or more independent streams
+    // in flight from its first instruction to its last; what is left of a longer clean tensor (universal (1,T) p
+    // against a (B,T) batch) follows in a clean-only loop.
+    const int64_t c4 = (NORM == NORM_L2) ? 0 : (a.clean_n >> 2);
+    const int Tc = a.clean_T;
+    int colc = 0, stepc = 0;
+    if (NORM == NORM_TV) { colc = (int)((tid * 4) % Tc); stepc = (int)((nth * 4) % Tc); }
+
+    // clean part of one float4 (every lane of the warp calls it for tv: the element after the float4 comes from the
+    // next lane by shuffle, only the last lane / the last float4 took it from memory in fetch)
+    auto clean_a = [&](const Raw4& raw, int64_t i4) {
+        if (NORM == NORM_SNR) {
+            if (i4 < c4) acc1 += (raw.c.x * raw.c.x + raw.c.y * raw.c.y) + (raw.c.z * raw.c.z + raw.c.w * raw.c.w);
+        } else if (NORM == NORM_TV) {
+            const bool act = i4 < c4;
+            const bool has_next = act && (i4 * 4 + 4 < a.clean_n);
+            float nx = __shfl_down_sync(0xffffffffu, raw.c.x, 1);
+            if (has_next && (lane == 31 || i4 + 1 >= c4)) nx = raw.nc;
+            if (act) acc1 += tv_quad(raw.c, nx, colc, Tc, has_next);
+            colc += stepc;
+            if (colc >= Tc) colc -= Tc;
+        }
+    };
     // phase A on one float4 whose operands are already in registers: step, accumulate the norm, hand back the
     // stepped values.  For tv every lane of the warp calls it (act = in range): the element after the float4 comes
     // from the next lane by shuffle, only the last lane (or the last float4) recomputes it from memory.
@@ -439,34 +460,50 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
             colp += stepp;
             if (colp >= a.T) colp -= a.T;
         }
+        clean_a(raw, i4);
         return x;
+    };
+    auto fetch_clean = [&](Raw4& r, int64_t i4) {
+        r.c = make_float4(0.f, 0.f, 0.f, 0.f);
+        r.nc = 0.f;
+        if (NORM != NORM_L2 && i4 < c4) {
+            r.c = ld4_stream(a.clean + i4 * 4);
+            if (NORM == NORM_TV && (lane == 31 || i4 + 1 >= c4) && i4 * 4 + 4 < a.clean_n) r.nc = a.clean[i4 * 4 + 4];
+        }
     };
     auto fetch = [&](int64_t i4, bool act) -> Raw4 {
         Raw4 r;
         r.p = r.g = r.m = r.v = make_float4(0.f, 0.f, 0.f, 0.f);
         r.np = r.ng = 0.f;
-        if (act) r = load_raw4<STEP>(a.p_in, i4 * 4, s);
+        if (act) load_raw4<STEP>(r, a.p_in, i4 * 4, s);
         if (NORM == NORM_TV && act && (lane == 31 || i4 + 1 >= n4) && i4 * 4 + 4 < a.n) {
             r.np = a.p_in[i4 * 4 + 4];
             if ((STEP & 3) != PAA_STEP_NONE) r.ng = ldg1<STEP>(s, i4 * 4 + 4);
         }
+        fetch_clean(r, i4);
         return r;
     };
 
-    {   // the first RCN float4s: all loads in flight at once, results stay in registers
-        Raw4 raw[RCN];
+    {   // the first RCN float4s, two at a time (six or more loads in flight per thread); results stay in registers
+        constexpr int G = 2;
+        static_assert(RCN % G == 0, "RCN is fetched in groups of G");
 #pragma unroll
-        for (int k = 0; k < RCN; ++k) raw[k] = fetch(tid + k * nth, tid + k * nth < n4);
+        for (int k0 = 0; k0 < RCN; k0 += G) {
+            Raw4 raw[G];
 #pragma unroll
-        for (int k = 0; k < RCN; ++k) {
-            const int64_t i4 = tid + k * nth;
-            const bool act = i4 < n4;
-            if (NORM == NORM_TV || act) keep[k] = phase_a(raw[k], i4, act);
+            for (int k = 0; k < G; ++k) raw[k] = fetch(tid + (k0 + k) * nth, tid + (k0 + k) * nth < n4);
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                const int64_t i4 = tid + (k0 + k) * nth;
+                const bool act = i4 < n4;
+                const float4 x = phase_a(raw[k], i4, act);
+                if (NORM == NORM_TV || act) keep[k0 + k] = x;
+            }
         }
     }
+    int64_t i4 = tid + RCN * nth;
     {   // the rest, software-pipelined two deep; (i4 - lane) is warp-uniform so whole warps stay for the shuffles
         int k = RCN;
-        int64_t i4 = tid + RCN * nth;
         Raw4 cur = fetch(i4, i4 < n4);
         while (i4 - lane < n4) {
             const int64_t i4n = i4 + nth;
@@ -481,6 +518,13 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
             i4 = i4n;
             ++k;
         }
+        // `cur` holds the (clean-only) float4 at i4, fetched but not consumed yet
+        if (NORM != NORM_L2 && i4 - lane < c4) {
+            clean_a(cur, i4);
+            i4 += nth;
+        } else if (NORM != NORM_L2) {
+            i4 += 0;
+        }
     }
     if (tid == 0) {                                         // the n % 4 trailing elements go through global memory
         for (int64_t i = n4 << 2; i < a.n; ++i) {
@@ -490,37 +534,24 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
             else if ((int)(i % a.T) != a.T - 1 && i + 1 < a.n) acc0 += fabsf(stepped1<STEP, false>(a.p_in, i + 1, s) - x);
         }
     }
-    if (NORM == NORM_SNR) {
-        const int64_t c4 = a.clean_n >> 2;
-#pragma unroll 4
-        for (int64_t i = tid; i < c4; i += nth) {
-            const float4 c = ld4_stream(a.clean + i * 4);
-            acc1 += (c.x * c.x + c.y * c.y) + (c.z * c.z + c.w * c.w);
+    if (NORM != NORM_L2) {
+        // what is left of the clean audio behind the perturbation's range (four float4 in flight per thread)
+        constexpr int U = 4;
+        while (i4 - lane < c4) {
+            Raw4 r[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) fetch_clean(r[u], i4 + u * nth);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i4 + u * nth - lane < c4) clean_a(r[u], i4 + u * nth);
+            i4 += U * nth;
         }
-        for (int64_t i = (c4 << 2) + tid; i < a.clean_n; i += nth) { const float c = a.clean[i]; acc1 += c * c; }
-    } else if (NORM == NORM_TV) {
-        const int64_t c4 = a.clean_n >> 2;
-        const int Tc = a.clean_T;
-        int colc = (int)((tid * 4) % Tc);
-        const int stepc = (int)((nth * 4) % Tc);
-#pragma unroll 4
-        for (int64_t i4 = tid; i4 - lane < c4; i4 += nth) {
-            const bool act = i4 < c4;
-            const int64_t i = i4 * 4;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            const bool has_next = act && (i + 4 < a.clean_n);
-            const bool from_mem = has_next && (lane == 31 || i4 + 1 >= c4);
-            float nxl = 0.f;
-            if (act) x = ld4_stream(a.clean + i);
-            if (from_mem) nxl = a.clean[i + 4];                 // issued together with the float4, not after the shuffle
-            float nx = __shfl_down_sync(0xffffffffu, x.x, 1);
-            if (from_mem) nx = nxl;
-            if (act) acc1 += tv_quad(x, nx, colc, Tc, has_next);
-            colc += stepc;
-            if (colc >= Tc) colc -= Tc;
+        if (NORM == NORM_SNR) {
+            for (int64_t i = (c4 << 2) + tid; i < a.clean_n; i += nth) { const float c = a.clean[i]; acc1 += c * c; }
+        } else {
+            for (int64_t i = (c4 << 2) + tid; i < a.clean_n; i += nth)
+                if ((int)(i % Tc) != Tc - 1 && i + 1 < a.clean_n) acc1 += fabsf(a.clean[i + 1] - a.clean[i]);
         }
-        for (int64_t i = (c4 << 2) + tid; i < a.clean_n; i += nth)
-            if ((int)(i % Tc) != Tc - 1 && i + 1 < a.clean_n) acc1 += fabsf(a.clean[i + 1] - a.clean[i]);
     }
     double wide[2] = {(double)acc0, (double)acc1};
     block_sum<2, kFT>(wide, a.partials + 2 * (int64_t)blockIdx.x);

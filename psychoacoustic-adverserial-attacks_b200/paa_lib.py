@@ -15,7 +15,8 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpaa.so")
+# PAA_LIBPAA: another build of the same library (kernel experiments under tools/); the default is the in-tree one
+LIB_PATH = os.environ.get("PAA_LIBPAA") or os.path.join(_HERE, "libpaa.so")
 
 # status codes of include/paa.h
 OK, ERR_NULL, ERR_SHAPE, ERR_UNSUPPORTED, ERR_CUDA, ERR_RANGE, ERR_NEED_CLEAN, ERR_ALIAS, ERR_NOLA, ERR_STATE = range(10)

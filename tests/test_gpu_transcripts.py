@@ -94,7 +94,15 @@ def test_transcripts_and_wer_identical(norm, opt):
 # oracle/transcript_check.py runs the reference arithmetic and libpaa side by side (teacher-forced: same p, same
 # gradient every step; free-running: each on its own trajectory) and reports every logit frame whose greedy token
 # differs, with the reference's top-1 minus top-2 margin on that frame.
-MARGIN = 1e-3      # logits are O(1); a frame whose two best tokens are closer than this is a numerical tie
+# Logits have std ~0.5.  The gradient source runs its cuDNN convolutions in TF32 (torch's default, which the reference
+# inherits): a last-bit fp32 difference in one waveform sample that crosses a TF32 rounding boundary moves the logits by
+# ~1e-3 (oracle/transcript_check.py).  Margins below are stated against that: teacher-forced flips may only happen on
+# frames whose two best tokens are closer than 5e-3 (1 % of the logit scale), free-running ones (sign(g) ties make the
+# trajectories drift by 2*lr on a small fraction of samples) closer than 2e-2; with the gradient source in full fp32
+# (cudnn_tf32=False) the bar is 2e-5.
+MARGIN = 5e-3
+MARGIN_FREE = 2e-2
+MARGIN_FP32 = 2e-5
 
 
 def base_model(dev):
@@ -106,7 +114,7 @@ def base_model(dev):
     return m
 
 
-def _identity_case(norm, B, sec, rows, opt, mode, steps, micro=0, **over):
+def _identity_case(norm, B, sec, rows, opt, mode, steps, micro=0, cudnn_tf32=None, free_running=True, **over):
     from oracle import paa_oracle as orc, transcript_check as tc
     from paa_b200.core import iso
     from paa_b200.training_utils import build, parser
@@ -125,24 +133,42 @@ def _identity_case(norm, B, sec, rows, opt, mode, steps, micro=0, **over):
     args.device = str(dev)
     thr = build.init_phon_threshold_tensor(args)
     rep = tc.run(model, clean, ["hello world this is a test"] * B, args, hp, steps, p0, orc.build_weight_interpolator(),
-                 iso.build_weight_interpolator(), thr, micro=micro)
+                 iso.build_weight_interpolator(), thr, micro=micro, cudnn_tf32=cudnn_tf32, free_running=free_running)
     print(rep)
     return rep, tc
+
+
+def _check_report(rep, tc, margin=MARGIN, margin_free=MARGIN_FREE):
+    tf, ctl = rep["teacher_forced"], rep["control_one_ulp"]
+    assert rep["max_rel_err_p_teacher_forced"] <= 1e-5
+    assert not tc.flips_above(tf, margin), tf
+    # WER counters (libpaa's C++ edit distance on libpaa's transcripts vs the oracle's DP on the reference's) never differ
+    assert tf["wer_mismatch_steps"] == 0
+    if tf["flips"] == 0:
+        assert tf["transcript_mismatch_steps"] == 0
+    # libpaa is no further from the reference than the reference is from itself after a one-ulp nudge
+    assert tf["flips"] <= 3 * ctl["flips"] + 10, (tf["flips"], ctl["flips"])
+    assert tf["max_logit_diff"] <= 3 * ctl["max_logit_diff"] + 1e-6
+    if "free_running" in rep:
+        fr = rep["free_running"]
+        assert not tc.flips_above(fr, margin_free), fr
+        assert fr["wer_mismatch_steps"] == 0
 
 
 @pytest.mark.parametrize("rows", [1, 32], ids=["universal", "per_utterance"])
 def test_wav2vec2_base_configs1_snr_transcripts_identical(rows):
     """BASELINE.json configs[1]: targeted 'delete' x5, snr 40 dB, PGD, batch 32 x 10 s, 20 steps."""
     rep, tc = _identity_case("snr", 32, 10, rows, "pgd", "targeted", 20)
-    tf, fr = rep["teacher_forced"], rep["free_running"]
-    assert rep["max_rel_err_p_teacher_forced"] <= 1e-5
-    assert not tc.flips_above(tf, MARGIN), tf
-    assert tf["frames"] == 20 * 32 * 499
-    if tf["flips"] == 0:
-        assert tf["transcript_mismatch_steps"] == 0 and tf["wer_mismatch_steps"] == 0
-    assert not tc.flips_above(fr, MARGIN), fr
-    if fr["flips"] == 0:
-        assert fr["transcript_mismatch_steps"] == 0 and fr["wer_mismatch_steps"] == 0
+    assert rep["teacher_forced"]["frames"] == 20 * 32 * 499
+    _check_report(rep, tc)
+
+
+def test_wav2vec2_base_configs1_fp32_gradient_source():
+    """The same with cuDNN's TF32 switched off (gradient source in full fp32): the logit differences drop by three
+    orders of magnitude, and so does the margin below which a frame can flip."""
+    rep, tc = _identity_case("snr", 32, 10, 1, "pgd", "targeted", 20, cudnn_tf32=False, free_running=False)
+    _check_report(rep, tc, margin=MARGIN_FP32)
+    assert rep["teacher_forced"]["max_logit_diff"] < 1e-4
 
 
 @pytest.mark.parametrize("norm,over", [("max_phon", {}), ("fletcher_munson", dict(fm_epsilon=2.0))])
@@ -151,22 +177,13 @@ def test_wav2vec2_base_configs2_stft_transcripts_identical(norm, over):
     call in chunks of 32), 20 steps (fletcher_munson: 6 -- the oracle's host interpolation dominates)."""
     steps = 20 if norm == "max_phon" else 6
     rep, tc = _identity_case(norm, 64, 15, 1, "pgd", "untargeted", steps, micro=32, **over)
-    tf, fr = rep["teacher_forced"], rep["free_running"]
-    assert rep["max_rel_err_p_teacher_forced"] <= 1e-5
-    assert not tc.flips_above(tf, MARGIN), tf
-    if tf["flips"] == 0:
-        assert tf["transcript_mismatch_steps"] == 0 and tf["wer_mismatch_steps"] == 0
-    assert not tc.flips_above(fr, MARGIN), fr
+    _check_report(rep, tc)
 
 
 def test_wav2vec2_base_adam_l2_transcripts_identical():
     """Adam (the reference's default optimiser) + l2 on wav2vec2-base, 16 x 10 s, universal p, 10 steps."""
-    rep, tc = _identity_case("l2", 16, 10, 1, "adam", "untargeted", 10, l2_size=0.5, lr=1e-3)
-    tf = rep["teacher_forced"]
-    assert rep["max_rel_err_p_teacher_forced"] <= 1e-5
-    assert not tc.flips_above(tf, MARGIN), tf
-    if tf["flips"] == 0:
-        assert tf["transcript_mismatch_steps"] == 0 and tf["wer_mismatch_steps"] == 0
+    rep, tc = _identity_case("l2", 16, 10, 1, "adam", "untargeted", 10, free_running=False, l2_size=0.5, lr=1e-3)
+    _check_report(rep, tc)
 
 
 def test_micro_batched_gradient_source_matches_whole_batch():
@@ -197,7 +214,15 @@ def test_micro_batched_gradient_source_matches_whole_batch():
                 r = train.train_epoch(args, loader, p0, model, 0, None, None, wer, None, optimizer)
                 res[micro] = (r.p.detach().clone(), r.avg_ctc, r.avg_wer, wer.errors, wer.words)
             a, b = res[0], res[3]
-            assert abs(a[1] - b[1]) <= 1e-5 * abs(a[1]) and a[2:] == b[2:]
-            # sign(g) of near-zero gradient elements may differ with the summation order; everything else is equal
-            differ = ((a[0] - b[0]).abs() > 1e-6 * a[0].abs().max()).float().mean()
-            assert float(differ) < (5e-3 if opt == "pgd" else 5e-2), (rows, opt, float(differ))
+            assert abs(a[1] - b[1]) <= 1e-4 * abs(a[1]) and a[2:] == b[2:]
+            if opt == "pgd":
+                # sign(g) of near-zero gradient elements may differ with the summation order; everything else is equal
+                differ = ((a[0] - b[0]).abs() > 1e-6 * a[0].abs().max()).float().mean()
+                assert float(differ) < 5e-3, (rows, opt, float(differ))
+            else:
+                # Adam's update lr * m_hat / (sqrt(v_hat) + eps) follows the gradient's magnitude, and the chunked model call
+                # (batch 3 instead of 8: other cuDNN algorithms, TF32 convolutions) moves the gradient by ~1e-3 relative:
+                # the two trajectories stay within 2 % of the distance travelled
+                start = (torch.randn(rows, T, generator=torch.Generator().manual_seed(2)) * 1e-3).to(dev)
+                rel = float((a[0] - b[0]).norm() / (a[0] - start).norm())
+                assert rel < 2e-2, (rows, opt, rel)
