@@ -104,6 +104,31 @@ int paa_create(int device, int n_fft, int hop, int sr, paa_handle** out) {
     e = cudaMalloc(&h->d_blob, h->blob_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_blob, blob.data(), h->blob_bytes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { int rc = paa_cuda_fail(h, e); paa_destroy(h); return rc; }
+    if (n_fft == 1024 && hop == 256) {
+        // tables of the half-warp kernel: forward twiddles W_512^{l k1} (cos, -sin) as [k1][l], the first half of the
+        // true Hann window (the second half is 1 - w), the reciprocal overlap-add envelope of an interior hop block
+        std::vector<float> b;
+        for (int k1 = 0; k1 < 32; ++k1)
+            for (int l = 0; l < 16; ++l) {
+                const double th = 2.0 * M_PI * (double)(l * k1) / 512.0;
+                b.push_back((float)std::cos(th));
+                b.push_back((float)(-std::sin(th)));
+            }
+        for (int i = 0; i < 512; ++i) b.push_back(h->h_window[i]);
+        for (int q = 0; q < hop; ++q) {
+            float env = 0.f;
+            for (int d = h->R - 1; d >= 0; --d) env = std::fmaf(h->h_window[d * hop + q], h->h_window[d * hop + q], env);
+            b.push_back(1.f / env);
+        }
+        h->blob_hw_smem = b.size() * 4;
+        h->off_hw_window = h->blob_hw_smem;
+        for (int i = 0; i < n_fft; ++i) b.push_back(h->h_window[i]);
+        e = cudaMalloc(&h->d_blob_hw, b.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_blob_hw, b.data(), b.size() * 4, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { int rc = paa_cuda_fail(h, e); paa_destroy(h); return rc; }
+        const char* env_hw = std::getenv("PAA_STFT_HW");
+        h->use_hw = (env_hw && env_hw[0] == '1') ? 1 : 0;      // opt-in: measured slower than k_stft at 8 warps/SM
+    }
     *out = h;
     return PAA_OK;
 }
@@ -111,6 +136,7 @@ int paa_create(int device, int n_fft, int hop, int sr, paa_handle** out) {
 int paa_destroy(paa_handle* h) {
     if (!h) return PAA_OK;
     cudaFree(h->d_blob);
+    cudaFree(h->d_blob_hw);
     cudaFree(h->d_fm_blob);
     delete h;
     return PAA_OK;

@@ -26,6 +26,12 @@ struct paa_handle {
     size_t off_twiddle = 0, off_post = 0, off_window = 0;
     std::vector<float> h_window;
 
+    // half-warp kernel (n_fft 1024, hop 256; paa_stft.cu k_stft_hw): [W_512^{l k1} float2[32][16] | window[0..511] |
+    // reciprocal envelope[hop]] is the part copied into shared memory (blob_hw_smem bytes); the full window follows
+    void* d_blob_hw = nullptr;
+    size_t blob_hw_smem = 0, off_hw_window = 0;
+    int use_hw = 0;          // 0 when the geometry has no half-warp kernel or PAA_STFT_HW=0 (A/B measurements)
+
     // fletcher_munson penalty grid, frequency axis pre-interpolated per rfft bin
     float* d_fm_blob = nullptr;      // [64: phon knots][n_phon x F: w(knot i, f_k)], fill outside the frequency axis
     size_t fm_blob_bytes = 0;

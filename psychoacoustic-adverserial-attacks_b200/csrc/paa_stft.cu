@@ -24,6 +24,7 @@
 #include <type_traits>
 #include <vector>
 #include "paa_fft.cuh"
+#include "paa_fft32.cuh"
 #include "paa_internal.h"
 
 namespace {
@@ -71,6 +72,9 @@ struct StftArgs {
     int fm_np, fm_uniform;
     float fm_fill, fm_k0, fm_inv_dk, fm_klast;
     double* partials;
+    // k_stft_hw: (cos, sin)(2 pi k / n_fft) and the full true Hann window, global memory
+    const void* post_table;
+    const float* win_full;
 };
 
 // ---- TMA 1-D bulk copy + mbarrier (PTX) -----------------------------------------------------
@@ -837,6 +841,420 @@ __global__ void __launch_bounds__(kThreadsStft, (NFFT == 1024 ? 2 : 3)) k_stft(S
     }
 }
 
+// ---- n_fft 1024, hop 256: the fused kernel on half warps (paa_fft32.cuh) --------------------------------------------
+// Same tile geometry, staging, overlap-add order and epilogue as k_stft<1024, SRC_TIME, SINK_TIME, OP>, but a frame
+// belongs to 16 lanes with 32 points each: a CTA is 4 warps = 8 half warps, half warp h runs the frames 4h .. 4h+3 of
+// the tile one after the other, and a warp instruction serves two frames that are four apart (they never touch the same
+// output samples).  Conventions that differ from k_stft:
+//   * Z is NOT halved by the window table (the table holds the true Hann window, which lets w[n + 512] = 1 - w[n] ride
+//     the first butterfly level: only 16 window values per lane and direction, read from shared memory where both half
+//     warps hit the same address).  The split therefore yields X2 = 2 X, and the operators fold 1/2048 instead of 2/1024.
+//   * blob = [W_512^{l k1} as float2[32][16] | first half of the window float[512] | reciprocal envelope float[256]].
+constexpr int kHwWarps = 4, kHwThreads = kHwWarps * 32, kHwHalf = 2 * kHwWarps;
+
+// X2 = 2 X[k] -> X'[k] / 1024 * 2  (what the merge wants: see the scaling note above; tbl = limit[k] / 1024)
+template <int OP>
+__device__ __forceinline__ cpx apply_op_hw(const StftArgs& a, const float* tbl, float scale, int k, cpx X2, bool& bad) {
+    constexpr float kC = 1.f / 2048.f;
+    if (OP == OP_MASK) return mul2(X2, bcast((k < a.k_lo || k >= a.k_hi) ? kC : 0.f));
+    if (OP == OP_SCALE) return mul2(X2, bcast(scale));              // caller pre-multiplies scale by 1/2048
+    if (OP == OP_PHON) {
+        float re, im;
+        up(X2, re, im);
+        const float P = fmaf(re, re, im * im);                      // 4 |X|^2
+        bad = bad || !(P > 1e-36f);
+        const float r = rsqrt_ftz(P);                               // 1 / (2 |X|)
+        const float xc = fmaf(P * r, kC, 1e-8f * 2.f * kC);         // (|X| + 1e-8) / 1024
+        return mul2(X2, bcast(fminf(xc, tbl[k]) * r));              // unit phasor X2 r; a NaN bin stays NaN through r
+    }
+    return mul2(X2, bcast(kC));
+}
+
+// lane 0 of a half warp holds the two self-paired butterflies k1 = 0 and 16: map their pairs onto the sixteen slots
+// (za[s], zb[15-s]) every other lane uses (tools/emulate_fft32.py: lane0_in / lane0_out)
+__device__ __forceinline__ void hw_lane0_in(cpx (&za)[16], cpx (&zb)[16]) {
+    cpx a[16], b[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { a[i] = za[i]; b[i] = zb[i]; }
+    zb[15] = a[8];
+#pragma unroll
+    for (int s = 1; s < 8; ++s) zb[15 - s] = a[16 - s];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { za[8 + i] = b[i]; zb[7 - i] = b[15 - i]; }
+}
+__device__ __forceinline__ void hw_lane0_out(cpx (&za)[16], cpx (&zb)[16]) {
+    cpx a[16], b[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { a[i] = za[i]; b[i] = zb[i]; }
+    za[8] = b[15];
+#pragma unroll
+    for (int s = 1; s < 8; ++s) za[16 - s] = b[15 - s];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { zb[i] = a[8 + i]; zb[15 - i] = b[7 - i]; }
+}
+
+// split -> per-bin operator -> merge on one thread's registers.  za[k2] = Z[lam + 32 k2], zb[k2] = Z[(32 - lam) + 32 k2]
+// (lane 0: Z[32 k2] and Z[16 + 32 k2]); slot s = (za[s], zb[15-s]) is the pair (k, N-k), k = lam + 32 s, split twiddle
+// e^{2 pi i k / 1024} = base(lam) e^{i pi s / 16}.  Returns true when OP_PHON met a bin the fast operator cannot serve.
+template <int OP, bool SLOW>
+__device__ __forceinline__ bool middle_hw(const StftArgs& a, cpx (&za)[16], cpx (&zb)[16], cpx base, const float* tbl, float scale,
+                                          int lam) {
+    constexpr int N = 512;
+    const bool l0 = lam == 0;
+    bool bad = false;
+    auto op = [&](cpx X2, int k, bool& flag) {
+        if (SLOW && OP == OP_PHON) {
+            float xr, xi;
+            up(X2, xr, xi);
+            xr *= 0.5f; xi *= 0.5f;                                  // the true X[k]
+            op_phon(tbl, k, 1.f / 1024.f, xr, xi);
+            return pk(xr, xi);
+        }
+        return apply_op_hw<OP>(a, tbl, scale, k, X2, flag);
+    };
+    auto pair = [&](cpx& zA, cpx& zB, int k, cpx w, bool dc) {
+        const int kn = N - k;
+        float wx, wy;
+        up(w, wx, wy);
+        const cpx zp = dc ? zA : zB;
+        //   E = za + conj(zb),  D = za - conj(zb),  T = (-i D) conj(w) = (-i D) wx + (-D) wy,  2 X[k] = E + T,  2 conj X[N-k] = E - T
+        const cpx E = add2(zA, conj2(zp)), D = sub2(zA, conj2(zp));
+        const cpx T = fma2(neg2(D), bcast(wy), mul2(rot90<-1>(D), bcast(wx)));
+        cpx X = op(add2(E, T), k, bad);
+        cpx Yc = op(sub2(E, T), kn, bad);
+        // inverse merge; irfft ignores the imaginary parts of the DC and Nyquist bins
+        X = pk(cre(X), dc ? 0.f : cim(X));
+        Yc = pk(cre(Yc), dc ? 0.f : cim(Yc));
+        //   A = X + conj(Y),  B = X - conj(Y),  p = w B,  Z'[k] = A + i p,  Z'[N-k] = conj(A) + swap(p)
+        const cpx A = add2(X, Yc), Bv = sub2(X, Yc);
+        const cpx p = fma2(rot90<+1>(Bv), bcast(wy), mul2(Bv, bcast(wx)));
+        zA = add2(A, rot90<+1>(p));
+        zB = add2(conj2(A), swap2(p));
+    };
+    if (l0) hw_lane0_in(za, zb);
+    // slots 8..15 of lane 0 hold bins 16 + 32 (s - 8) = 32 s - 240: own bin offset and twiddle base e^{-2 pi i 240 / 1024}
+    const int kB = l0 ? -240 : lam;
+    const cpx baseB = l0 ? pk(0.09801714032956060f, -0.99518472667219689f) : base;
+    {   // slot 0: a normal pair for lanes 1..15; lane 0 runs the DC/Nyquist unit on za and the N/2 unit on zb
+        const cpx half_in = zb[15];
+        pair(za[0], zb[15], lam, base, l0);
+        bool bad_h = false;
+        const cpx Xh = op(mul2(conj2(half_in), bcast(2.f)), N / 2, bad_h);       // 2 X[N/2] = 2 conj Z[N/2]
+        bad = bad || (l0 && bad_h);
+        if (l0) zb[15] = mul2(conj2(Xh), bcast(2.f));
+    }
+#pragma unroll
+    for (int s = 1; s < 16; ++s) {
+        const cpx bs = s < 8 ? base : baseB;
+        const cpx w = fma2(rot90<+1>(bs), bcast(s32(s)), mul2(bs, bcast(c32(s))));          // base * e^{i pi s / 16}
+        pair(za[s], zb[15 - s], (s < 8 ? lam : kB) + 32 * s, w, false);
+    }
+    if (l0) hw_lane0_out(za, zb);
+    return bad;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kHwThreads, 2) k_stft_hw(StftArgs a) {
+    constexpr int NFFT = 1024, N = 512, F = N + 1, HOP = 256, R = 4, FT = kHwHalf * R, S = FT - R + 1;
+    constexpr int LIN = (FT - 1) * HOP + NFFT;                  // staged input span (floats)
+    static_assert(LIN * 4 == kHwHalf * kHwBuf * 8, "the gradient span is staged in the exchange buffers");
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ float red[kHwWarps];
+    __shared__ int s_done[kHwWarps];            // overlap-add phases each warp has completed
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, hl = lane & 15, hw = tid >> 4;
+
+    unsigned char* sp = smem;
+    const cpx* s_tw = (const cpx*)sp;                          // W_512^{l k1}, [k1][l]
+    const cpx* s_win = (const cpx*)(sp + 4096);                // window pairs (w[2m], w[2m+1]), m = 0..255
+    const float* s_renv = (const float*)(sp + 4096 + 2048);    // reciprocal window envelope of an interior hop block
+    sp += a.blob_bytes;
+    float* s_thr = (float*)sp;
+    if (OP == OP_PHON) sp += ((F * 4 + 15) / 16) * 16;
+    cpx* s_fft = (cpx*)sp;
+    sp += (size_t)kHwHalf * kHwBuf * 8;
+    float* s_in = (float*)sp;
+    sp += (size_t)LIN * 4;
+    float* s_ola = (float*)sp;
+
+    const int row = blockIdx.x / a.tiles_per_row, ti = blockIdx.x % a.tiles_per_row;
+    const int t0 = ti * S - R / 2 + 1;
+    const int in0 = t0 * HOP - NFFT / 2;
+    const float* xr = a.x + (size_t)row * a.T;
+    const float* gr = a.grad ? a.grad + (size_t)row * a.T : nullptr;
+    const bool tma_stage = a.vec_ok && in0 >= 0 && in0 + LIN <= a.T;
+
+    if (tid == 0) mbar_init(&bar, 1);
+    if (tid < kHwWarps) s_done[tid] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, a.blob_bytes + (tma_stage ? (unsigned)LIN * 4u * (gr ? 2u : 1u) : 0u));
+        tma_bulk_g2s(smem, a.blob, a.blob_bytes, &bar);
+        if (tma_stage) {
+            tma_bulk_g2s(s_in, xr + in0, (unsigned)LIN * 4u, &bar);
+            if (gr) tma_bulk_g2s(s_fft, gr + in0, (unsigned)LIN * 4u, &bar);
+        }
+    }
+    if (!tma_stage) {           // row-end tiles: reflect padding, PGD step fused (as in k_stft)
+        const int T = a.T;
+        constexpr int kStageUnroll = 6;
+        constexpr int lin4 = LIN / 4;
+        for (int base4 = 0; base4 < lin4; base4 += kStageUnroll * kHwThreads) {
+            float4 pv[kStageUnroll], gv[kStageUnroll];
+            bool fast[kStageUnroll];
+#pragma unroll
+            for (int u = 0; u < kStageUnroll; ++u) {
+                const int i4 = base4 + u * kHwThreads + tid, s = in0 + i4 * 4;
+                fast[u] = i4 < lin4 && a.vec_ok && s >= 0 && s + 3 < T;
+                pv[u] = gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (fast[u]) {
+                    pv[u] = *reinterpret_cast<const float4*>(xr + s);
+                    if (gr) gv[u] = *reinterpret_cast<const float4*>(gr + s);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kStageUnroll; ++u) {
+                const int i4 = base4 + u * kHwThreads + tid;
+                if (i4 >= lin4) continue;
+                const int i = i4 * 4, s = in0 + i;
+                float4 v = pv[u];
+                if (fast[u]) {
+                    if (gr) {
+                        const float4 g = gv[u];
+                        v.x += a.lr * ((float)(g.x > 0.f) - (float)(g.x < 0.f));
+                        v.y += a.lr * ((float)(g.y > 0.f) - (float)(g.y < 0.f));
+                        v.z += a.lr * ((float)(g.z > 0.f) - (float)(g.z < 0.f));
+                        v.w += a.lr * ((float)(g.w > 0.f) - (float)(g.w < 0.f));
+                    }
+                } else {
+                    float e[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        int sc = s + c;
+                        if (sc < 0) sc = -sc;
+                        if (sc >= T) sc = 2 * (T - 1) - sc;
+                        sc = min(max(sc, 0), T - 1);
+                        float val = xr[sc];
+                        if (gr) { const float g = gr[sc]; val += a.lr * ((float)(g > 0.f) - (float)(g < 0.f)); }
+                        e[c] = val;
+                    }
+                    v = make_float4(e[0], e[1], e[2], e[3]);
+                }
+                *reinterpret_cast<float4*>(s_in + i) = v;
+            }
+        }
+    }
+    for (int i4 = tid; i4 < S * HOP / 4; i4 += kHwThreads) *reinterpret_cast<float4*>(s_ola + i4 * 4) = make_float4(0, 0, 0, 0);
+    if (a.pf_stride > 0) {      // the tile this slot's next CTA will stage: HBM -> L2 now
+        const int nb = blockIdx.x + a.pf_stride;
+        if (nb < (int)gridDim.x) {
+            const int nrow = nb / a.tiles_per_row, nti = nb % a.tiles_per_row;
+            const int nin0 = (nti * S - R / 2 + 1) * HOP - NFFT / 2;
+            const int lo = max(nin0, 0), hi = min(nin0 + LIN, a.T);
+            const float* px = a.x + (size_t)nrow * a.T;
+            const float* pg = a.grad ? a.grad + (size_t)nrow * a.T : nullptr;
+            for (int s = lo + tid * 32; s < hi; s += kHwThreads * 32) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(px + s));
+                if (pg) asm volatile("prefetch.global.L2 [%0];" ::"l"(pg + s));
+            }
+        }
+    }
+    float scale = 1.f;
+    if (OP == OP_SCALE) scale = a.scalars[PAA_S_SCALE] * (1.f / 2048.f);
+    if (OP == OP_PHON) {        // thr[k] = spl_thresh[k] - max(spl_thresh) + reference_db, kept as a magnitude / 1024
+        float mx = -INFINITY;
+        for (int k = tid; k < F; k += kHwThreads) mx = fmaxf(mx, a.spl_thresh[k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) red[warp] = mx;
+        __syncthreads();
+        mx = red[0];
+#pragma unroll
+        for (int w = 1; w < kHwWarps; ++w) mx = fmaxf(mx, red[w]);
+        for (int k = tid; k < F; k += kHwThreads) {
+            const float thr = (a.spl_thresh[k] - mx) + a.ref_db;
+            s_thr[k] = exp10f(thr / 20.f) * (1.f / 1024.f);
+        }
+    }
+    // this lane's split-twiddle base e^{2 pi i lam / 1024}, straight from the global table of the handle
+    const float2 pbf = __ldg(reinterpret_cast<const float2*>(a.post_table) + hl);
+    const cpx post_base = pk(pbf.x, pbf.y);
+    mbar_wait(&bar, 0);
+    if (tma_stage && gr) {      // PGD step on the staged span, in shared memory (the gradient sits in the exchange buffers)
+        const float4* g4 = reinterpret_cast<const float4*>(s_fft);
+        float4* p4 = reinterpret_cast<float4*>(s_in);
+        const float lr = a.lr;
+        for (int i4 = tid; i4 < LIN / 4; i4 += kHwThreads) {
+            float4 v = p4[i4];
+            const float4 g = g4[i4];
+            v.x += lr * ((float)(g.x > 0.f) - (float)(g.x < 0.f));
+            v.y += lr * ((float)(g.y > 0.f) - (float)(g.y < 0.f));
+            v.z += lr * ((float)(g.z > 0.f) - (float)(g.z < 0.f));
+            v.w += lr * ((float)(g.w > 0.f) - (float)(g.w < 0.f));
+            p4[i4] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- frames ----------------------------------------------------------------------------------
+    cpx* buf = s_fft + (size_t)hw * kHwBuf;
+    cpx* bcol = buf + hl;                                   // row accesses: bcol[kHwRow * k1]
+    cpx* brow0 = buf + kHwRow * hl;                         // column accesses of butterfly j0 = lam: brow0[l]
+    cpx* brow1 = buf + kHwRow * hw_j1(hl);                  //                              j1
+    const cpx* twl = s_tw + hl;                             // twl[16 k1] = W_512^{l k1} (forward: cos, -sin)
+    const cpx* winl = s_win + hl;                           // winl[16 q], q = 0..15
+    constexpr int olim = S * HOP;
+    for (int r = 0; r < R; ++r) {
+        const int f = hw * R + r;
+        const int t = t0 + f;
+        const bool live = t >= 0 && t < a.n_frames;         // per half warp
+        if (__any_sync(0xffffffffu, live)) {
+        const int obase = (f - R + 1) * HOP;                // owned-region coordinate of frame sample 0
+        cpx* ola = reinterpret_cast<cpx*>(s_ola + obase) + hl;     // only dereferenced inside [0, olim)
+        const bool inside = live && obase >= 0 && obase + NFFT <= olim;
+        const cpx* x2 = reinterpret_cast<const cpx*>(s_in + f * HOP) + hl;
+        cpx za[16], zb[16];
+        bool slow = false;
+        for (;;) {
+            {   // forward: window + DFT-32 over q (the window rides the first butterfly level: w[n + 512] = 1 - w[n])
+                cpx v[32];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const cpx x0 = x2[16 * b], x1 = x2[16 * (b + 8)], xh0 = x2[16 * (b + 16)], xh1 = x2[16 * (b + 24)];
+                    const cpx w0 = winl[16 * b], w1 = winl[16 * (b + 8)];
+                    // y_q + y_{q+16} = x_{q+16} + w (x_q - x_{q+16}),   y_q - y_{q+16} = w (x_q + x_{q+16}) - x_{q+16}
+                    const cpx u0 = fma2(w0, sub2(x0, xh0), xh0), u1 = fma2(w0, add2(x0, xh0), neg2(xh0));
+                    const cpx u2 = fma2(w1, sub2(x1, xh1), xh1), u3 = fma2(w1, add2(x1, xh1), neg2(xh1));
+                    v[b] = add2(u0, u2);
+                    v[16 + b] = sub2(u0, u2);
+                    v[8 + b] = add2(u1, rot90<-1>(u3));
+                    v[24 + b] = sub2(u1, rot90<-1>(u3));
+                }
+                dft32_tail<-1>(v);
+                // column hl of the buffer belongs to this lane on either side of the forward store, and rows j0 / j1 on
+                // either side of the inverse store: only the two transposes themselves need a warp barrier
+#pragma unroll
+                for (int k1 = 0; k1 < 32; ++k1) {
+                    cpx o = v[hw_out32(k1)];
+                    if (k1 > 0) { const cpx w = twl[16 * k1]; o = cmul_tw<-1>(o, cre(w), cim(w)); }
+                    bcol[kHwRow * k1] = o;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int l = 0; l < 16; ++l) { za[l] = brow0[l]; zb[l] = brow1[l]; }
+                dft16<-1>(za);
+                dft16<-1>(zb);
+            }
+            bool bad;
+            if (OP == OP_PHON && slow) bad = middle_hw<OP, true>(a, za, zb, post_base, s_thr, scale, hl);
+            else bad = middle_hw<OP, false>(a, za, zb, post_base, s_thr, scale, hl);
+            // a zero / denormal / NaN bin somewhere in a live frame (rare): redo with the exact operator
+            if (OP != OP_PHON || slow || !__any_sync(0xffffffffu, bad && live)) break;
+            slow = true;
+        }
+        // overlap-add ordering: warp w adds phase r only after warp w+1 has finished phase r-1 (see k_stft)
+        if (r > 0 && warp + 1 < kHwWarps) {
+            if (lane == 0) {
+                int done;
+                do {
+                    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(done) : "r"(smem_u32(&s_done[warp + 1])) : "memory");
+                } while (done < r);
+            }
+            __syncwarp();
+        }
+        {   // inverse: IDFT-16 over k2 -> exchange -> conj twiddle -> IDFT-32 over k1 -> windowed overlap-add
+            dft16<+1>(za);
+            dft16<+1>(zb);
+#pragma unroll
+            for (int l = 0; l < 16; ++l) { brow0[l] = za[l]; brow1[l] = zb[l]; }
+            __syncwarp();
+            cpx v[32];
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) {
+                cpx o = bcol[kHwRow * k1];
+                if (k1 > 0) { const cpx w = twl[16 * k1]; o = cmul_tw<+1>(o, cre(w), cim(w)); }
+                v[k1] = o;
+            }
+            dft32<+1>(v);
+            const bool all_in = __all_sync(0xffffffffu, inside);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const cpx w = winl[16 * q];
+                const cpx y0 = v[hw_out32(q)], y1 = v[hw_out32(q + 16)];
+                const cpx c1 = fma2(neg2(w), y1, y1);               // (1 - w) y
+                if (all_in) {
+                    ola[16 * q] = fma2(y0, w, ola[16 * q]);
+                    ola[16 * (q + 16)] = add2(ola[16 * (q + 16)], c1);
+                } else if (live) {
+                    const int o0 = obase + 2 * (hl + 16 * q), o1 = o0 + 512;
+                    if (o0 >= 0 && o0 < olim) ola[16 * q] = fma2(y0, w, ola[16 * q]);
+                    if (o1 >= 0 && o1 < olim) ola[16 * (q + 16)] = add2(ola[16 * (q + 16)], c1);
+                }
+            }
+        }
+        }
+        __syncwarp();                               // publish: this warp's phase-r contributions are in place
+        if (lane == 0) asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(&s_done[warp])), "r"(r + 1) : "memory");
+    }
+    __syncthreads();
+
+    // ---- epilogue: y[n] = ola[n] / sum_t w^2, zero past hop (T'-1), pad / crop to out_len (as k_stft) -----------------
+    {
+        const float* g_win = a.win_full;
+        float* yr = a.y + (size_t)row * a.out_len;
+        const bool vec = (a.out_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15u) == 0);
+        constexpr int hop4 = HOP >> 2, n4 = S * hop4;
+        constexpr int kEpi = 4;
+        for (int e0 = tid; e0 < n4; e0 += kEpi * kHwThreads) {
+            float4 o[kEpi], rv[kEpi];
+            int nn[kEpi];
+            bool livee[kEpi];
+#pragma unroll
+            for (int u = 0; u < kEpi; ++u) {
+                const int e = e0 + u * kHwThreads;
+                const int jb = e / hop4, q = (e - jb * hop4) * 4;
+                const int gb = ti * S + jb;
+                nn[u] = gb * HOP + q;
+                livee[u] = e < n4 && nn[u] < a.out_len;
+                o[u] = rv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!livee[u]) continue;
+                const int ub = gb + R / 2;                                    // newest frame covering this block
+                const bool exists = gb < a.n_frames - 1;
+                const bool interior = ub - R + 1 >= 0 && ub <= a.n_frames - 1;
+                if (!exists) continue;
+                o[u] = *reinterpret_cast<const float4*>(s_ola + jb * HOP + q);
+                if (interior) {
+                    rv[u] = *reinterpret_cast<const float4*>(s_renv + q);
+                } else {
+                    float ev[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int d = R - 1; d >= 0; --d) {
+                        const int tt = ub - d;
+                        if (tt < 0 || tt >= a.n_frames) continue;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { const float wv = __ldg(g_win + d * HOP + q + c); ev[c] = fmaf(wv, wv, ev[c]); }
+                    }
+                    rv[u] = make_float4(1.f / ev[0], 1.f / ev[1], 1.f / ev[2], 1.f / ev[3]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kEpi; ++u) {
+                if (!livee[u]) continue;
+                const float4 v = make_float4(o[u].x * rv[u].x, o[u].y * rv[u].y, o[u].z * rv[u].z, o[u].w * rv[u].w);
+                const int n = nn[u];
+                if (vec && n + 3 < a.out_len) {
+                    *reinterpret_cast<float4*>(yr + n) = v;
+                } else {
+                    if (n < a.out_len) yr[n] = v.x;
+                    if (n + 1 < a.out_len) yr[n + 1] = v.y;
+                    if (n + 2 < a.out_len) yr[n + 2] = v.z;
+                    if (n + 3 < a.out_len) yr[n + 3] = v.w;
+                }
+            }
+        }
+    }
+}
+
 // ---- fletcher_munson finalize: norm = sqrt(sum), scale = norm <= eps ? 1 : eps / max(norm, 1e-8) ---
 // projections.py:130-132.  torch's clamp(min=1e-8) propagates NaN (a NaN norm makes the whole output NaN); fmaxf
 // would not, so the NaN case is kept explicit.
@@ -1003,6 +1421,27 @@ int launch(paa_handle* h, StftArgs& a, int grid, cudaStream_t st) {
     return PAA_OK;
 }
 
+// n_fft 1024 / hop 256: the half-warp kernel (same tile geometry: 32 frames, 29 owned hop blocks)
+template <int OP>
+int launch_hw(paa_handle* h, StftArgs& a, int grid, cudaStream_t st) {
+    a.blob = h->d_blob_hw; a.blob_bytes = (unsigned)h->blob_hw_smem;
+    a.post_table = (const unsigned char*)h->d_blob + h->off_post;
+    a.win_full = reinterpret_cast<const float*>((const unsigned char*)h->d_blob_hw + h->off_hw_window);
+    a.pf_stride = h->num_sms * 2;
+    size_t smem = h->blob_hw_smem + (OP == OP_PHON ? ((h->F * 4 + 15) / 16) * 16 : 0) + (size_t)kHwHalf * kHwBuf * 8 +
+                  (size_t)((a.frames_per_tile - 1) * h->hop + 1024) * 4 + (size_t)a.blocks_per_tile * h->hop * 4;
+    auto kern = k_stft_hw<OP>;
+    static int granted[64];
+    const int dev = h->device & 63;
+    if ((size_t)__atomic_load_n(&granted[dev], __ATOMIC_ACQUIRE) < smem) {
+        PAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        __atomic_store_n(&granted[dev], (int)smem, __ATOMIC_RELEASE);
+    }
+    kern<<<grid, kHwThreads, smem, st>>>(a);
+    PAA_LAUNCH_CHECK(h);
+    return PAA_OK;
+}
+
 template <int SRC, int SINK, int OP>
 int launch_n(paa_handle* h, StftArgs& a, int grid, cudaStream_t st) {
     if (h->n_fft == 1024) return launch<1024, SRC, SINK, OP>(h, a, grid, st);
@@ -1084,6 +1523,7 @@ int run_fused(paa_handle* h, StftArgs& a, const float* src, const float* grad, f
     a.vec_ok = aligned16(src) && (T % 4 == 0) && (!grad || aligned16(grad));
     const int out_blocks = (out_len + h->hop - 1) / h->hop;
     a.tiles_per_row = std::max(1, (out_blocks + a.blocks_per_tile - 1) / a.blocks_per_tile);
+    if (h->use_hw) return launch_hw<OP>(h, a, rows * a.tiles_per_row, st);
     return launch_n<SRC_TIME, SINK_TIME, OP>(h, a, rows * a.tiles_per_row, st);
 }
 

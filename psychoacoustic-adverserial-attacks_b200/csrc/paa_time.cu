@@ -4,6 +4,7 @@
 // deterministic block -> grid reductions (no float atomics), device-side branch on the norm so
 // the host never synchronises.
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include <cmath>
 #include "paa_internal.h"
 
@@ -640,7 +641,9 @@ __global__ void __launch_bounds__(kThreads) k_sum_parts(StepDev s, float* out, i
 // ---- kernels: compose + clamp (train.py:136) and its backward -- the input side of the path ----
 //   forward : x_adv[b,t] = clamp(clean[b,t] + p[b or 0, t], -1, 1)
 //   backward: dL/dp[b or 0, t] = (sum over b of) dL/dx_adv[b,t] * 1[-1 <= clean[b,t] + p[.,t] <= 1]   (torch's clamp mask)
-// grid.x covers float4 columns, grid.y strides over rows; a universal (1,T) p is re-read from L2, never from HBM.
+// grid.x covers float4 columns, grid.y strides over rows, four rows per trip and (the host sizes grid.y so) ONE trip per CTA:
+// measured on B200, the finest decomposition wins (5 024 CTAs for 128 x 10 s: 32.9 us against 34.9 us with 1 256 CTAs and
+// 36.9 us with exactly one resident wave); a universal (1,T) p is re-read from L2, never from HBM.
 template <bool VEC>
 __global__ void __launch_bounds__(kThreads) k_compose(const float* __restrict__ clean, const float* __restrict__ p,
                                                      float* __restrict__ out, int rows, int p_rows, int T) {
@@ -685,41 +688,77 @@ __device__ __forceinline__ float pass1(float x, float q, float g) {
     return (s >= -1.f && s <= 1.f) ? g : 0.f;                  // NaN input: mask false, as torch's comparison
 }
 
+// per-utterance p: element-wise, 2-D grid as the forward
 template <bool VEC>
 __global__ void __launch_bounds__(kThreads) k_compose_bwd(const float* __restrict__ clean, const float* __restrict__ p,
-                                                         const float* __restrict__ gx, float* __restrict__ gp,
-                                                         int rows, int p_rows, int T) {
+                                                         const float* __restrict__ gx, float* __restrict__ gp, int rows, int T) {
     const int W = VEC ? 4 : 1;
     const int cols = (T + W - 1) / W;
-    for (int c = blockIdx.x * kThreads + threadIdx.x; c < cols; c += gridDim.x * kThreads) {
-        if (p_rows == 1) {
-            // universal perturbation: sum over the batch in row order (fixed, deterministic)
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (VEC) q = ld4(p + (size_t)c * 4); else q.x = p[c];
-#pragma unroll 8
-            for (int b = 0; b < rows; ++b) {
-                const size_t i = (size_t)b * T + (size_t)c * W;
-                if (VEC) {
-                    const float4 x = ld4_stream(clean + i), g = ld4_stream(gx + i);
-                    acc.x += pass1(x.x, q.x, g.x); acc.y += pass1(x.y, q.y, g.y);
-                    acc.z += pass1(x.z, q.z, g.z); acc.w += pass1(x.w, q.w, g.w);
-                } else {
-                    acc.x += pass1(clean[i], q.x, gx[i]);
-                }
-            }
-            if (VEC) st4(gp + (size_t)c * 4, acc); else gp[c] = acc.x;
-        } else {
-            for (int b = blockIdx.y; b < rows; b += gridDim.y) {
-                const size_t i = (size_t)b * T + (size_t)c * W;
-                if (VEC) {
-                    const float4 x = ld4_stream(clean + i), q = ld4(p + i), g = ld4_stream(gx + i);
-                    st4(gp + i, make_float4(pass1(x.x, q.x, g.x), pass1(x.y, q.y, g.y), pass1(x.z, q.z, g.z), pass1(x.w, q.w, g.w)));
-                } else {
-                    gp[i] = pass1(clean[i], p[i], gx[i]);
-                }
+    for (int c = blockIdx.x * kThreads + threadIdx.x; c < cols; c += gridDim.x * kThreads)
+        for (int b = blockIdx.y; b < rows; b += gridDim.y) {
+            const size_t i = (size_t)b * T + (size_t)c * W;
+            if (VEC) {
+                const float4 x = ld4_stream(clean + i), q = ld4(p + i), g = ld4_stream(gx + i);
+                st4(gp + i, make_float4(pass1(x.x, q.x, g.x), pass1(x.y, q.y, g.y), pass1(x.z, q.z, g.z), pass1(x.w, q.w, g.w)));
+            } else {
+                gp[i] = pass1(clean[i], p[i], gx[i]);
             }
         }
+}
+
+// universal (1,T) p: dL/dp[t] = sum over the batch.  The batch is split over the CTAs of a thread-block cluster
+// (cluster = (1, K, 1): K CTAs share a column range, CTA y takes the rows y, y + K, ...), each thread keeps its column's
+// partial sum in registers, and the K partials meet in the leader's registers through distributed shared memory in rank
+// order: one launch, no scratch, no atomics, a fixed summation order (bit-identical from run to run).
+constexpr int kCuThreads = 128;
+template <bool VEC>
+__global__ void __launch_bounds__(kCuThreads) k_compose_bwd_u(const float* __restrict__ clean, const float* __restrict__ p,
+                                                             const float* __restrict__ gx, float* __restrict__ gp, int rows, int T) {
+    constexpr int W = VEC ? 4 : 1;
+    __shared__ float4 part[kCuThreads];
+    cg::cluster_group cl = cg::this_cluster();
+    const int K = (int)gridDim.y, rank = (int)blockIdx.y;       // the cluster spans the whole y extent
+    const int cols = (T + W - 1) / W;
+    const int c = blockIdx.x * kCuThreads + threadIdx.x;
+    const bool on = c < cols;
+    const size_t col = (size_t)(on ? c : 0) * W;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) {
+        if (VEC) {
+            constexpr int U = 8;
+            const float4 q = ld4(p + col);
+            for (int b0 = rank; b0 < rows; b0 += U * K) {
+                float4 x[U], g[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (b0 + u * K < rows) {
+                        const size_t i = (size_t)(b0 + u * K) * T + col;
+                        x[u] = ld4_stream(clean + i); g[u] = ld4_stream(gx + i);
+                    }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (b0 + u * K < rows) {
+                        acc.x += pass1(x[u].x, q.x, g[u].x); acc.y += pass1(x[u].y, q.y, g[u].y);
+                        acc.z += pass1(x[u].z, q.z, g[u].z); acc.w += pass1(x[u].w, q.w, g[u].w);
+                    }
+            }
+        } else {
+            const float q = p[col];
+            for (int b = rank; b < rows; b += K) acc.x += pass1(clean[(size_t)b * T + col], q, gx[(size_t)b * T + col]);
+        }
+    }
+    if (K > 1) {
+        if (rank != 0) part[threadIdx.x] = acc;
+        cl.sync();
+        if (rank == 0)
+            for (int r = 1; r < K; ++r) {
+                const float4 o = *cl.map_shared_rank(&part[threadIdx.x], r);
+                acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            }
+        cl.sync();                                             // the leader has read every partial: the others may exit
+    }
+    if (on && rank == 0) {
+        if (VEC) st4(gp + col, acc); else gp[col] = acc.x;
     }
 }
 
@@ -1016,10 +1055,10 @@ int paa_project_tv(paa_handle* h, const float* p_in, float* p_out, int rows, int
                                    (float)tv_epsilon, 0.0, step, scratch, (cudaStream_t)stream);
 }
 
-static dim3 compose_grid(const paa_handle* h, int cols, int rows, bool row_parallel) {
+static dim3 compose_grid(const paa_handle* h, int cols, int rows, int rows_per_trip) {
     const int gx = std::max(1, std::min((cols + kThreads - 1) / kThreads, h->num_sms * kBlocksPerSm));
-    int gy = 1;
-    if (row_parallel) gy = std::max(1, std::min(rows, (h->num_sms * kBlocksPerSm + gx - 1) / gx));
+    const int gy = std::max(1, std::min(rows, rows_per_trip > 0 ? (rows + rows_per_trip - 1) / rows_per_trip
+                                                                  : (h->num_sms * kBlocksPerSm + gx - 1) / gx));
     return dim3(gx, gy, 1);
 }
 
@@ -1029,12 +1068,38 @@ int paa_compose_clamp(paa_handle* h, const float* clean, int clean_rows, const f
     if (!h || !clean || !p || !x_adv) return PAA_ERR_NULL;
     if (clean_rows <= 0 || T <= 0 || (p_rows != 1 && p_rows != clean_rows)) return PAA_ERR_SHAPE;
     const bool vec = aligned16(clean) && aligned16(p) && aligned16(x_adv) && (T % 4 == 0);
-    const dim3 grid = compose_grid(h, vec ? T / 4 : T, clean_rows, true);
+    const dim3 grid = compose_grid(h, vec ? T / 4 : T, clean_rows, 4);
     if (vec) k_compose<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(clean, p, x_adv, clean_rows, p_rows, T);
     else k_compose<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(clean, p, x_adv, clean_rows, p_rows, T);
     PAA_LAUNCH_CHECK(h);
     return PAA_OK;
 }
+
+}  // extern "C"
+
+template <bool VEC>
+static int launch_compose_bwd_u(paa_handle* h, const float* clean, const float* p, const float* gx, float* gp, int rows, int T,
+                                cudaStream_t st) {
+    const int cols = VEC ? T / 4 : T;
+    const int gxb = (cols + kCuThreads - 1) / kCuThreads;
+    // measured on B200 (tools/ab_time.py, 32 x 10 s / 128 x 10 s): K = 2: 11.1 / 28.8 us, K = 4: 13.7 / 30.3, K = 8: 18.5 / 34.0
+    // (the cluster barrier grows with K), the single-CTA column loop of round 1: 16.4 / 51.1
+    const int K = rows >= 2 ? 2 : 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(gxb, K, 1);
+    cfg.blockDim = dim3(kCuThreads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = K; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    PAA_CUDA(h, cudaLaunchKernelEx(&cfg, k_compose_bwd_u<VEC>, clean, p, gx, gp, rows, T));
+    PAA_LAUNCH_CHECK(h);
+    return PAA_OK;
+}
+
+extern "C" {
 
 int paa_compose_clamp_backward(paa_handle* h, const float* clean, int clean_rows, const float* p, int p_rows, int T,
                                const float* grad_x_adv, float* grad_p, void* stream) {
@@ -1042,9 +1107,13 @@ int paa_compose_clamp_backward(paa_handle* h, const float* clean, int clean_rows
     if (!h || !clean || !p || !grad_x_adv || !grad_p) return PAA_ERR_NULL;
     if (clean_rows <= 0 || T <= 0 || (p_rows != 1 && p_rows != clean_rows)) return PAA_ERR_SHAPE;
     const bool vec = aligned16(clean) && aligned16(p) && aligned16(grad_x_adv) && aligned16(grad_p) && (T % 4 == 0);
-    const dim3 grid = compose_grid(h, vec ? T / 4 : T, clean_rows, p_rows != 1);
-    if (vec) k_compose_bwd<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(clean, p, grad_x_adv, grad_p, clean_rows, p_rows, T);
-    else k_compose_bwd<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(clean, p, grad_x_adv, grad_p, clean_rows, p_rows, T);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p_rows == 1 && clean_rows > 1)
+        return vec ? launch_compose_bwd_u<true>(h, clean, p, grad_x_adv, grad_p, clean_rows, T, st)
+                   : launch_compose_bwd_u<false>(h, clean, p, grad_x_adv, grad_p, clean_rows, T, st);
+    const dim3 grid = compose_grid(h, vec ? T / 4 : T, clean_rows, 0);
+    if (vec) k_compose_bwd<true><<<grid, kThreads, 0, st>>>(clean, p, grad_x_adv, grad_p, clean_rows, T);
+    else k_compose_bwd<false><<<grid, kThreads, 0, st>>>(clean, p, grad_x_adv, grad_p, clean_rows, T);
     PAA_LAUNCH_CHECK(h);
     return PAA_OK;
 }
