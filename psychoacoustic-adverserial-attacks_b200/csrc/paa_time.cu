@@ -414,10 +414,13 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     int colp = 0, stepp = 0;
     if (NORM == NORM_TV) { colp = (int)((tid * 4) % a.T); stepp = (int)((nth * 4) % a.T); }
 
-    // The clean audio (snr: sum of squares, tv: total variation) rides the same loop as the perturbation: float4 i4 of
-    // p, grad (Adam: m, v) and clean are requested together, so every thread keeps three or more independent streams
-    // in flight from its first instruction to its last; what is left of a longer clean tensor (universal (1,T) p
-    // against a (B,T) batch) follows in a clean-only loop.
+    // tv: the clean audio rides the same loop as the perturbation -- float4 i4 of p, grad and clean are requested
+    // together, so every thread keeps three independent streams in flight (93.6 us against 96.1 us at 128 x 10 s);
+    // what is left of a longer clean tensor (universal (1,T) p against a (B,T) batch) follows in a clean-only loop with
+    // four float4 in flight per thread.  snr takes the clean-only loop for all of it: riding costs it registers in the
+    // Adam form and measured 2.4 % slower (22.4 against 21.9 us at 32 x 10 s), the deeper clean loop alone is what made
+    // the universal shape faster (12.0 against 14.3 us).
+    constexpr bool kRide = NORM == NORM_TV;
     const int64_t c4 = (NORM == NORM_L2) ? 0 : (a.clean_n >> 2);
     const int Tc = a.clean_T;
     int colc = 0, stepc = 0;
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
             colp += stepp;
             if (colp >= a.T) colp -= a.T;
         }
-        clean_a(raw, i4);
+        if (kRide) clean_a(raw, i4);
         return x;
     };
     auto fetch_clean = [&](Raw4& r, int64_t i4) {
@@ -481,7 +484,7 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
             r.np = a.p_in[i4 * 4 + 4];
             if ((STEP & 3) != PAA_STEP_NONE) r.ng = ldg1<STEP>(s, i4 * 4 + 4);
         }
-        fetch_clean(r, i4);
+        if (kRide) fetch_clean(r, i4);
         return r;
     };
 
@@ -520,13 +523,12 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
             ++k;
         }
         // `cur` holds the (clean-only) float4 at i4, fetched but not consumed yet
-        if (NORM != NORM_L2 && i4 - lane < c4) {
+        if (kRide && i4 - lane < c4) {
             clean_a(cur, i4);
             i4 += nth;
-        } else if (NORM != NORM_L2) {
-            i4 += 0;
         }
     }
+    if (!kRide) i4 = tid;
     if (tid == 0) {                                         // the n % 4 trailing elements go through global memory
         for (int64_t i = n4 << 2; i < a.n; ++i) {
             const float x = stepped1<STEP, NORM != NORM_TV>(a.p_in, i, s);
