@@ -399,7 +399,7 @@ constexpr int kFT = 512;
 constexpr int kRC = 4;
 constexpr int kSCMax = 12;
 
-template <int NORM, int STEP>
+template <int NORM, int STEP, bool RIDE>
 __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, FinalArgs f, int sc_iters) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ float4 cache[];                       // [sc_iters][kFT]
@@ -417,10 +417,11 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     // tv: the clean audio rides the same loop as the perturbation -- float4 i4 of p, grad and clean are requested
     // together, so every thread keeps three independent streams in flight (93.6 us against 96.1 us at 128 x 10 s);
     // what is left of a longer clean tensor (universal (1,T) p against a (B,T) batch) follows in a clean-only loop with
-    // four float4 in flight per thread.  snr takes the clean-only loop for all of it: riding costs it registers in the
-    // Adam form and measured 2.4 % slower (22.4 against 21.9 us at 32 x 10 s), the deeper clean loop alone is what made
-    // the universal shape faster (12.0 against 14.3 us).
-    constexpr bool kRide = NORM == NORM_TV;
+    // four float4 in flight per thread.  snr rides only when the clean tensor is longer than the perturbation (the
+    // universal shape, latency bound: the first clean loads leave with the kernel's first instruction, 12.0 against
+    // 14.3 us at (1,T) x 32 x 10 s); with one row per utterance riding costs registers and measured 2.4 % slower
+    // (22.4 against 21.9 us), so that shape keeps the clean-only loop (RIDE = false).
+    constexpr bool kRide = RIDE;
     const int64_t c4 = (NORM == NORM_L2) ? 0 : (a.clean_n >> 2);
     const int Tc = a.clean_T;
     int colc = 0, stepc = 0;
@@ -800,13 +801,13 @@ int launch_reduce(paa_handle* h, const ReduceArgs& a, const StepDev& sd, int gri
     return PAA_OK;
 }
 
-// The cooperative kernel of one (NORM, STEP): its dynamic shared-memory ceiling is raised and its co-residency queried
+// The cooperative kernel of one (NORM, STEP, RIDE): its dynamic shared-memory ceiling is raised and its co-residency queried
 // once per device (not per call: small shapes are launch-latency bound), the answers cached per instantiation.
 constexpr int kMaxDevices = 64;
-template <int NORM, int STEP>
-cudaError_t fused_kernel(const paa_handle* h, void** kern, int* blocks_per_sm) {
+template <int NORM, int STEP, bool RIDE>
+cudaError_t fused_kernel_r(const paa_handle* h, void** kern, int* blocks_per_sm) {
     static int cached[kMaxDevices];          // 0 = unknown, else 1 + blocks per SM
-    void* k = (void*)k_fused<NORM, STEP>;
+    void* k = (void*)k_fused<NORM, STEP, RIDE>;
     *kern = k;
     const int dev = h->device & (kMaxDevices - 1);
     int c = __atomic_load_n(&cached[dev], __ATOMIC_ACQUIRE);
@@ -821,6 +822,14 @@ cudaError_t fused_kernel(const paa_handle* h, void** kern, int* blocks_per_sm) {
     }
     *blocks_per_sm = c - 1;
     return cudaSuccess;
+}
+
+// tv always rides; snr when asked to (clean longer than the perturbation); l2 has no clean tensor
+template <int NORM, int STEP>
+cudaError_t fused_kernel(const paa_handle* h, bool ride, void** kern, int* blocks_per_sm) {
+    if (NORM == NORM_TV) return fused_kernel_r<NORM, STEP, NORM == NORM_TV>(h, kern, blocks_per_sm);
+    if (NORM == NORM_SNR && ride) return fused_kernel_r<NORM, STEP, NORM == NORM_SNR>(h, kern, blocks_per_sm);
+    return fused_kernel_r<NORM, STEP, false>(h, kern, blocks_per_sm);
 }
 
 template <int NORM>
@@ -877,12 +886,13 @@ int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int
         void* kern = nullptr;
         int bps = 0;
         cudaError_t e = cudaSuccess;
+        const bool ride = a.clean_n > n;
         switch (step_code(mode, sd)) {
-            case PAA_STEP_NONE: e = fused_kernel<NORM, PAA_STEP_NONE>(h, &kern, &bps); break;
-            case PAA_STEP_PGD: e = fused_kernel<NORM, PAA_STEP_PGD>(h, &kern, &bps); break;
-            case PAA_STEP_ADAM: e = fused_kernel<NORM, PAA_STEP_ADAM>(h, &kern, &bps); break;
-            case PAA_STEP_PGD | kStepParts: e = fused_kernel<NORM, PAA_STEP_PGD | kStepParts>(h, &kern, &bps); break;
-            default: e = fused_kernel<NORM, PAA_STEP_ADAM | kStepParts>(h, &kern, &bps); break;
+            case PAA_STEP_NONE: e = fused_kernel<NORM, PAA_STEP_NONE>(h, ride, &kern, &bps); break;
+            case PAA_STEP_PGD: e = fused_kernel<NORM, PAA_STEP_PGD>(h, ride, &kern, &bps); break;
+            case PAA_STEP_ADAM: e = fused_kernel<NORM, PAA_STEP_ADAM>(h, ride, &kern, &bps); break;
+            case PAA_STEP_PGD | kStepParts: e = fused_kernel<NORM, PAA_STEP_PGD | kStepParts>(h, ride, &kern, &bps); break;
+            default: e = fused_kernel<NORM, PAA_STEP_ADAM | kStepParts>(h, ride, &kern, &bps); break;
         }
         if (e != cudaSuccess) return paa_cuda_fail(h, e);
         if (bps > 0) {

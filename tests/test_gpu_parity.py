@@ -170,6 +170,23 @@ def test_long_rows_interior_tiles(norm, sigma, T, env):
     close(paa.step_and_project(p.cuda(), grad.cuda(), clean.cuda(), args, env["it_gpu"], thr_g), want)
 
 
+def test_half_warp_kernel_variant_passes_the_same_parity_tests():
+    """k_stft_hw (paa_fft32.cuh: one frame per 16 lanes, one shared-memory exchange per transform) is opt-in -- it measured
+    slower than k_stft -- but stays a correct implementation of the same projections: the golden,
+    differential and long-row parity tests of this file are re-run in a child process with PAA_STFT_HW=1 (the switch is
+    read when a handle is created)."""
+    import os
+    import subprocess
+    import sys
+    env_hw = dict(os.environ, PAA_STFT_HW="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "(golden_projection or long_rows_interior or oracle_differential or stress_bit) and "
+                              "(max_phon or min_max_freqs or fletcher_munson or stress)"],
+                       env=env_hw, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-500:]
+
+
 @pytest.mark.parametrize("norm,sigma", [("max_phon", 0.03), ("min_max_freqs", 0.01), ("fletcher_munson", 0.1)])
 def test_long_rows_adam(norm, sigma, env):
     """Adam + STFT-domain projection on rows with interior and row-end tiles: three steps through the drop-in

@@ -203,7 +203,8 @@ def test_micro_batched_gradient_source_matches_whole_batch():
             res = {}
             for micro in (0, 3):
                 args = parser.create_arg_parser().parse_args(["--norm_type", "l2", "--optimizer_type", opt, "--lr", "1e-3",
-                                                              "--l2_size", "0.5", "--micro_batch", str(micro)])
+                                                              "--l2_size", "50", "--micro_batch", str(micro)])   # never binds: a binding
+                # projection rescales EVERY sample when a handful of sign(g) ties flip, which is not what is compared here
                 args.device = str(dev)
                 p0 = (torch.randn(rows, T, generator=torch.Generator().manual_seed(2)) * 1e-3).to(dev)
                 optimizer = None

@@ -25,22 +25,10 @@ only = set(sys.argv[1:])
 tag = os.path.basename(os.environ.get("PAA_LIBPAA", "libpaa.so")) + (" hw" if os.environ.get("PAA_STFT_HW") == "1" else "")
 peak, _ = bench.measured_peak()
 interp = iso.build_weight_interpolator()
-FOOT = 600e6          # bytes the rotating sets cover together
+FOOT = bench.SUSTAINED_FOOTPRINT          # bytes the rotating sets cover together
 
 
-def timed(calls, reps):
-    for c in calls:
-        c()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda._sleep(10_000_000)
-    e0.record()
-    for _ in range(reps):
-        for c in calls:
-            c()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3 / (reps * len(calls))      # us per call
+timed = bench.sustained_us      # back to back on rotating cold input sets inside one event pair
 
 
 for name, B, sec, rows, sigma, opt in bench.SWEEP_CASES:
