@@ -595,11 +595,24 @@ def compose_sweep(dev, flush, peak, iters):
             tf_ms, xt = timed(lambda: (clean + p).clamp_(-1.0, 1.0))
             tb_ms, _ = timed(lambda: torch.autograd.grad(xt, p, w, retain_graph=True))
             fb, bb = 8 * B * T + 4 * rows * T, 8 * B * T + 8 * rows * T       # algorithmic bytes: fwd R clean,p W x; bwd R clean,g,p W gp
+            # sustained: back to back on rotating cold input sets (sustained_us)
+            nsets = max(2, min(24, math.ceil(SUSTAINED_FOOTPRINT / fb)))
+            sets = [(clean, w, p)]
+            for _ in range(nsets - 1):
+                sets.append(((torch.rand(B, T, generator=g, device=dev) * 2 - 1) * 0.9, torch.randn(B, T, generator=g, device=dev),
+                             (torch.randn(rows, T, generator=g, device=dev) * 0.3).requires_grad_(True)))
+            f_us = sustained_us([(lambda q=q: compose_clamp(q[0], q[2])) for q in sets], max(2, 60 // nsets))
+            xs = [compose_clamp(q[0], q[2]) for q in sets]
+            b_us = sustained_us([(lambda q=q, y=y: torch.autograd.grad(y, q[2], q[1], retain_graph=True)) for q, y in zip(sets, xs)],
+                                max(2, 60 // nsets))
+            del sets, xs
             tag = ("universal" if rows == 1 else "per_utterance") + ("" if B == 32 else f"_{B}x10s")
             res[f"compose_fwd_{tag}"] = {"shape": f"{B}x{SECONDS}s", "ms": round(fwd_ms, 4), "GB/s": round(fb / fwd_ms / 1e6, 1),
-                                         "frac_of_measured_peak": round(fb / fwd_ms / 1e6 / peak, 4), "torch_eager_ms": round(tf_ms, 4)}
+                                         "frac_of_measured_peak": round(fb / fwd_ms / 1e6 / peak, 4), "torch_eager_ms": round(tf_ms, 4),
+                                         "sustained_us": round(f_us, 2), "sustained_frac": round(fb / f_us / 1e3 / peak, 4)}
             res[f"compose_bwd_{tag}"] = {"shape": f"{B}x{SECONDS}s", "ms": round(bwd_ms, 4), "GB/s": round(bb / bwd_ms / 1e6, 1),
-                                         "frac_of_measured_peak": round(bb / bwd_ms / 1e6 / peak, 4), "torch_eager_ms": round(tb_ms, 4)}
+                                         "frac_of_measured_peak": round(bb / bwd_ms / 1e6 / peak, 4), "torch_eager_ms": round(tb_ms, 4),
+                                         "sustained_us": round(b_us, 2), "sustained_frac": round(bb / b_us / 1e3 / peak, 4)}
             del p, x, xt
         del clean, w
         torch.cuda.empty_cache()
