@@ -173,9 +173,10 @@ int paa_set_fm_grid(paa_handle* h, const double* phon_knots, int n_phon, const d
     if (n_phon < 2 || n_freq < 2 || n_phon > 32) return PAA_ERR_SHAPE;      // table must fit shared memory next to the tile
     for (int i = 1; i < n_phon; ++i) if (!(phon_knots[i] > phon_knots[i - 1])) return PAA_ERR_SHAPE;
     for (int j = 1; j < n_freq; ++j) if (!(freq_knots[j] > freq_knots[j - 1])) return PAA_ERR_SHAPE;
-    // blob = [64 floats: knots][n_phon rows of F floats]; rows are contiguous in k so a warp's lanes (consecutive
+    // blob = [64 floats: knots][n_phon rows of paa_fm_stride(F) floats]; rows are contiguous in k so a warp's lanes (consecutive
     // bins) read neighbouring words, and the whole table rides the kernel's TMA bulk copy into shared memory
-    const size_t blob_floats = ((64 + (size_t)n_phon * h->F + 3) / 4) * 4;
+    const int FS = paa_fm_stride(h->F);
+    const size_t blob_floats = ((64 + (size_t)n_phon * FS + 3) / 4) * 4;
     std::vector<float> blob(blob_floats, 0.f);
     for (int k = 0; k < h->F; ++k) {
         const double f = (double)((float)k * h->bin_hz);         // the reference queries with fp32 bin centres
@@ -184,7 +185,7 @@ int paa_set_fm_grid(paa_handle* h, const double* phon_knots, int n_phon, const d
         while (j + 1 < n_freq - 1 && freq_knots[j + 1] < f) ++j;   // searchsorted(left) - 1, clipped
         const double t = (f - freq_knots[j]) / (freq_knots[j + 1] - freq_knots[j]);
         for (int i = 0; i < n_phon; ++i)
-            blob[64 + (size_t)i * h->F + k] =
+            blob[64 + (size_t)i * FS + k] =
                 inband ? (float)((1.0 - t) * values[i * n_freq + j] + t * values[i * n_freq + j + 1]) : (float)fill_value;
     }
     bool uniform = true;

@@ -33,13 +33,18 @@ struct paa_handle {
     int use_hw = 0;          // 0 when the geometry has no half-warp kernel or PAA_STFT_HW=0 (A/B measurements)
 
     // fletcher_munson penalty grid, frequency axis pre-interpolated per rfft bin
-    float* d_fm_blob = nullptr;      // [64: phon knots][n_phon x F: w(knot i, f_k)], fill outside the frequency axis
+    float* d_fm_blob = nullptr;      // [64: phon knots][n_phon rows of paa_fm_stride(F): w(knot i, f_k)], fill outside the frequency axis
     size_t fm_blob_bytes = 0;
     int fm_n_phon = 0;
     float fm_fill = 1.f;
     int fm_uniform = 0;              // knots equally spaced -> direct cell lookup
     float fm_k0 = 0.f, fm_klast = 0.f, fm_inv_dk = 0.f;
 };
+
+// Row stride of the fletcher_munson table: a multiple of 32 floats, so that the shared-memory bank of w(knot i, f_k) is
+// k mod 32 = the lane whatever knot row i a lane's level selects (F = 513 itself would make it (i + k) mod 32: two-way
+// conflicts wherever neighbouring bins fall into different 10-phon cells).
+constexpr int paa_fm_stride(int F) { return (F + 31) / 32 * 32; }
 
 // ---- status helpers -------------------------------------------------------------------------
 static inline int paa_cuda_fail(const paa_handle* h, cudaError_t e) {

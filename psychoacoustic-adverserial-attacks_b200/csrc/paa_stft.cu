@@ -67,7 +67,7 @@ struct StftArgs {
     float2* spec_out;
     long long sb, sf, st;
     // fletcher_munson
-    const float* fm_blob;  // [64 floats: phon knots][fm_np x F floats: w(knot i, f_k), out-of-band bins = fill]
+    const float* fm_blob;  // [64 floats: phon knots][fm_np rows of paa_fm_stride(F) floats: w(knot i, f_k), out-of-band bins = fill]
     unsigned fm_blob_bytes;
     int fm_np, fm_uniform;
     float fm_fill, fm_k0, fm_inv_dk, fm_klast;
@@ -274,9 +274,9 @@ __device__ __forceinline__ bool spectral_middle(const StftArgs& a, cpx* buf, con
             Yc = pk(y.x, -y.y);
         }
         if (SINK == SINK_REDUCE) {
-            const float t0 = fm_term<true>(a, tbl, N + 1, k, cre(X), cim(X));
+            const float t0 = fm_term<true>(a, tbl, paa_fm_stride(N + 1), k, cre(X), cim(X));
             if (commit) acc += t0;
-            if (!SELF) acc += fm_term<true>(a, tbl, N + 1, kn, cre(Yc), -cim(Yc));
+            if (!SELF) acc += fm_term<true>(a, tbl, paa_fm_stride(N + 1), kn, cre(Yc), -cim(Yc));
             return;
         }
         if (SLOW && OP == OP_PHON) {
@@ -415,8 +415,8 @@ __device__ __forceinline__ bool middle_paired(const StftArgs& a, cpx (&z)[2][8],
             Yc = pk(y.x, -y.y);
         }
         if (SINK == SINK_REDUCE) {
-            acc += fm_term<true>(a, tbl, N + 1, k, cre(X), cim(X));
-            acc += fm_term<true>(a, tbl, N + 1, kn, cre(Yc), -cim(Yc));
+            acc += fm_term<true>(a, tbl, paa_fm_stride(N + 1), k, cre(X), cim(X));
+            acc += fm_term<true>(a, tbl, paa_fm_stride(N + 1), kn, cre(Yc), -cim(Yc));
             return;
         }
         X = op(X, k, bad);
@@ -448,7 +448,7 @@ __device__ __forceinline__ bool middle_paired(const StftArgs& a, cpx (&z)[2][8],
         if (SRC == SRC_TIME) Xh = mul2(conj2(half_in), bcast(2.f));
         else { const float2 x = a.spec_in[spec_off + (long long)(l0 ? N / 2 : lane) * a.sf]; Xh = pk(x.x, x.y); }
         if (SINK == SINK_REDUCE) {
-            const float t = fm_term<true>(a, tbl, N + 1, N / 2, cre(Xh), cim(Xh));
+            const float t = fm_term<true>(a, tbl, paa_fm_stride(N + 1), N / 2, cre(Xh), cim(Xh));
             if (l0) acc += t;
         } else {
             bool bad_h = false;
@@ -1376,7 +1376,7 @@ __global__ void k_spec_fm_partials(StftArgs a, int F) {
         if (a.sf <= a.st) { k = (int)(i % F); t = (int)((i / F) % a.n_frames); b = (int)(i / ((long long)F * a.n_frames)); }
         else { t = (int)(i % a.n_frames); k = (int)((i / a.n_frames) % F); b = (int)(i / ((long long)F * a.n_frames)); }
         const float2 X = a.spec_in[b * a.sb + k * a.sf + t * a.st];
-        acc += fm_term<false>(a, a.fm_blob, F, k, X.x, X.y);
+        acc += fm_term<false>(a, a.fm_blob, paa_fm_stride(F), k, X.x, X.y);
     }
     __shared__ float sh[32];
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);

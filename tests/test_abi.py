@@ -88,6 +88,12 @@ def test_wer_counts():
     assert L.wer_counts(["a b c", "hello world"], ["a x c d", ""]) == (4, 5)
     assert L.wer_counts(["  spaced   out  "], ["spaced out"]) == (0, 2)
     assert L.wer_counts([], []) == (0, 0)
+    # known answers worked by hand (jiwer / HF evaluate are not in the image): word-level Levenshtein, summed over pairs
+    assert L.wer_counts(["the cat sat on the mat"], ["the cat sit on mat"]) == (2, 6)         # 1 substitution + 1 deletion
+    assert L.wer_counts(["a b c d"], ["b c d e"]) == (2, 4)                                  # 1 deletion + 1 insertion
+    assert L.wer_counts(["hello"], [""]) == (1, 1)                                           # everything deleted
+    assert L.wer_counts(["one two three"], ["one two three four five"]) == (2, 3)            # insertions count against the reference length
+    assert L.wer_counts(["delete delete delete delete delete"] * 2, ["delete", "x y z"]) == (4 + 5, 10)
     from paa_b200.core.loss_helpers import WerMetric
     m = WerMetric()
     assert m.compute(predictions=["a"], references=["a b"]) == 0.5
