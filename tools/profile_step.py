@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--no-model", action="store_true")
 ap.add_argument("--norms", default="linf,l2,snr,tv,min_max_freqs,max_phon,fletcher_munson")
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--compose", action="store_true", help="also one compose + clamp forward / backward per p shape at 128 x 10 s")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.cuda.set_device(0)
@@ -30,9 +31,9 @@ if not a.no_model:
     model = bench.build_model(dev)
     for q in model.parameters():
         q.requires_grad_(False)
-    clean, p0 = bench.synth(0, bench.BATCH, T, dev, bench.BATCH)
+    clean, p0 = bench.synth(0, bench.C1_BATCH, T, dev, bench.C1_BATCH)
     clean = clean.to(dev)
-    labels = loss_helpers.encode_labels(["delete delete delete delete delete"] * bench.BATCH, dev)
+    labels = loss_helpers.encode_labels(["delete delete delete delete delete"] * bench.C1_BATCH, dev)
     p = paa_b200.perturbation_constraint(p0.to(dev), clean, args, None, None)
     for it in range(2):
         p = p.detach().requires_grad_(True)
@@ -63,3 +64,17 @@ for norm in a.norms.split(","):
         torch.cuda.synchronize()
     print(f"{norm:16s} {B}x{sec}s  {e0.elapsed_time(e1) * 1e3:9.1f} us", flush=True)
     del clean, p, grad
+
+if a.compose:
+    from paa_b200.core.compose import compose_clamp  # noqa: E402
+    B, T = 128, 10 * bench.SR
+    g = torch.Generator(device=dev).manual_seed(7)
+    clean = (torch.rand(B, T, generator=g, device=dev) * 2 - 1) * 0.9
+    w = torch.randn(B, T, generator=g, device=dev)
+    for rows in (1, B):
+        p = (torch.randn(rows, T, generator=g, device=dev) * 0.3).requires_grad_(True)
+        for r in range(2):
+            x = compose_clamp(clean, p)
+            torch.autograd.grad(x, p, w)
+        torch.cuda.synchronize()
+        print(f"compose fwd+bwd  p_rows {rows}", flush=True)
