@@ -191,7 +191,9 @@ int paa_spec_fm_project(paa_handle* h, const float* spec_in, float* spec_out, in
 int paa_compose_clamp(paa_handle* h, const float* clean, int clean_rows, const float* p, int p_rows, int T,
                       float* x_adv, void* stream);
 /* its backward: grad_p[b or 0, t] = (sum over b of) grad_x_adv[b,t] * 1[-1 <= clean[b,t]+p[.,t] <= 1]  (torch's clamp mask);
- * for a universal (1,T) p the batch is summed in row order. */
+ * for a universal (1,T) p the batch is summed in a fixed order (even rows in row order + odd rows in row order: the two
+ * CTAs of a thread-block cluster each take one half and meet through distributed shared memory), so the result is
+ * bit-identical from run to run and within rounding of torch's own batch sum. */
 int paa_compose_clamp_backward(paa_handle* h, const float* clean, int clean_rows, const float* p, int p_rows, int T,
                                const float* grad_x_adv, float* grad_p, void* stream);
 
