@@ -177,7 +177,9 @@ class Plan:
         h = C.c_void_p()
         check(lib.paa_create(device.index, self.n_fft, self.hop, self.sr, C.byref(h)))
         self.h = h
-        self._scratch: Optional[torch.Tensor] = None
+        # caller-owned scratch of the C ABI, one buffer per CUDA stream that has used this plan: concurrent calls on
+        # different streams never share partials / scalars / staging (include/paa.h: re-entrant with distinct scratch)
+        self._scratch_by_stream = {}
         self._fm_obj = None              # the installed interpolator itself: a live reference, so its id cannot be reused
         self._fm_sig = None
 
@@ -187,11 +189,26 @@ class Plan:
         except Exception:
             pass
 
+    def _scratch_tensor(self, need: int = 0) -> torch.Tensor:
+        key = stream_ptr(self.device)
+        buf = self._scratch_by_stream.get(key)
+        if buf is None or buf.numel() < need:
+            with torch.cuda.device(self.device):
+                buf = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)   # allocated on the current stream
+            self._scratch_by_stream.pop(key, None)
+            self._scratch_by_stream[key] = buf
+            while len(self._scratch_by_stream) > 4:          # ephemeral streams: keep the four most recent buffers (a
+                self._scratch_by_stream.pop(next(iter(self._scratch_by_stream)))     # dropped one is freed in stream order)
+        return buf
+
+    @property
+    def _scratch(self) -> torch.Tensor:
+        """The scratch buffer of the current stream (scalars of its last reducing call live at the front)."""
+        return self._scratch_tensor()
+
     def scratch(self, rows: int, T: int) -> int:
         need = int(lib.paa_scratch_bytes(self.h, int(rows), int(T)))
-        if self._scratch is None or self._scratch.numel() < need:
-            self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._scratch.data_ptr()
+        return self._scratch_tensor(need).data_ptr()
 
     def scalars(self) -> np.ndarray:
         """The PAA_S_* scalars of the last reducing call (synchronises the current stream)."""

@@ -123,3 +123,37 @@ def test_cuda_graph_capture(norm):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, paa_b200.step_and_project(p, grad, clean, args, None, thr))
+
+
+def test_two_streams_share_a_plan_without_sharing_scratch():
+    """include/paa.h: entry points are re-entrant as long as concurrent calls use distinct scratch.  The Python binding
+    keeps one scratch buffer per CUDA stream, so two streams can drive the same (device, n_fft, hop) plan at once: the
+    reducing norms (partials + scalars in scratch) and fletcher_munson (staging buffer + tile partials in scratch) are
+    launched back to back on two streams, repeatedly, and must reproduce their single-stream results bit for bit."""
+    import paa_b200
+    from paa_b200.core import iso
+    from paa_b200.training_utils import build, parser
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    it = iso.build_weight_interpolator()
+    jobs = []
+    for norm, B, T, sigma in (("l2", 16, 160000, 0.01), ("snr", 8, 160000, 0.01), ("fletcher_munson", 6, 120000, 0.1),
+                              ("tv", 12, 80000, 0.01), ("max_phon", 4, 100000, 0.03)):
+        args = parser.create_arg_parser().parse_args(["--norm_type", norm, "--optimizer_type", "pgd", "--snr_db", "40"])
+        args.device = str(dev)
+        clean = (torch.rand(B, T, generator=g, device=dev) * 2 - 1) * 0.1
+        p = torch.randn(B, T, generator=g, device=dev) * sigma
+        grad = torch.randn(B, T, generator=g, device=dev)
+        thr = build.init_phon_threshold_tensor(args)
+        want = paa_b200.step_and_project(p, grad, clean, args, it, thr).clone()
+        jobs.append((args, clean, p, grad, thr, want))
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    for rep in range(6):
+        outs = []
+        for k, (args, clean, p, grad, thr, want) in enumerate(jobs):
+            with torch.cuda.stream(s1 if (k + rep) % 2 == 0 else s2):
+                outs.append(paa_b200.step_and_project(p, grad, clean, args, it, thr))
+        torch.cuda.synchronize()
+        for (args, *_rest, want), out in zip(jobs, outs):
+            assert torch.equal(out, want), (rep, args.norm_type)

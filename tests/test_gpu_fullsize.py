@@ -129,3 +129,26 @@ def test_fletcher_munson_per_utterance_512x10s():
     valid = 256 * (T // 256)
     assert rel_max(out[:, :valid], p[:, :valid] * float(s[L.S_SCALE])) < 1e-5
     assert float(out[:, valid:].abs().max()) == 0.0 if valid < T else True
+
+
+@pytest.mark.parametrize("norm,B,sec,sigma", [s for s in SHAPES if s[0] != "linf"])
+def test_baseline_shapes_bitwise_repeatable(norm, B, sec, sigma):
+    """compute-sanitizer (racecheck) is closed on this pool, so at BASELINE's full shapes every reducing / overlap-adding
+    kernel is run 12 times on the same inputs -- interleaved with a call on OTHER inputs that reuses the same scratch and
+    shared-memory state -- and every result must equal the first one bit for bit (grid barrier and partial re-sum of
+    k_fused, neighbour-warp overlap-add flags and tile halos of k_stft, the two launches of fletcher_munson)."""
+    import paa_b200
+    from oracle import paa_oracle as orc
+    from paa_b200.core import iso
+    T = sec * SR
+    clean, p, grad = _inputs(B, T, B, sigma, 99)
+    clean2, p2, grad2 = _inputs(B, T, B, sigma * 0.5, 100)
+    hp = orc.Hyper(norm_type=norm, optimizer_type="pgd", snr_db=40.0, device="cuda")
+    args = make_args(hp)
+    thr = thr_gpu(args)
+    it_gpu = iso.build_weight_interpolator()
+    first = paa_b200.step_and_project(p, grad, clean, args, it_gpu, thr).clone()
+    for _ in range(12):
+        paa_b200.step_and_project(p2, grad2, clean2, args, it_gpu, thr)
+        again = paa_b200.step_and_project(p, grad, clean, args, it_gpu, thr)
+        assert torch.equal(again, first), norm
