@@ -4,6 +4,7 @@
 // deterministic block -> grid reductions (no float atomics), device-side branch on the norm so
 // the host never synchronises.
 #include <cooperative_groups.h>
+#include <type_traits>
 #include <cstdlib>
 #include <cmath>
 #include "paa_internal.h"
@@ -377,6 +378,13 @@ __global__ void __launch_bounds__(kThreads) k_scale(const float* q_in, float* p_
 // |x1-x0| + |x2-x1| + |x3-x2| + |next-x3| for the float4 whose first element sits in column `col` of a row of
 // length T >= 4; a pair is dropped when its left element is the last sample of a row (projections.py:58,62).
 __device__ __forceinline__ float tv_quad(float4 x, float nx, int col, int T, bool has_next) {
+    if ((T & 3) == 0) {
+        // rows are whole float4s (every BASELINE shape): the three inner pairs never leave the row, only the pair with the
+        // next float4 can (kernel-uniform branch; 10 instructions less per float4 than the general form below)
+        float t = (fabsf(x.y - x.x) + fabsf(x.z - x.y)) + fabsf(x.w - x.z);
+        if (col + 4 != T && has_next) t += fabsf(nx - x.w);
+        return t;
+    }
     int c1 = col + 1, c2 = col + 2, c3 = col + 3;
     if (c1 >= T) c1 -= T;
     if (c2 >= T) c2 -= T;
@@ -403,8 +411,15 @@ template <int NORM, int STEP, bool RIDE>
 __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, FinalArgs f, int sc_iters) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ float4 cache[];                       // [sc_iters][kFT]
-    const int64_t tid = (int64_t)blockIdx.x * kFT + threadIdx.x, nth = (int64_t)gridDim.x * kFT;
-    const int64_t n4 = a.n >> 2;
+    // tv indexes its float4s with 32 bits (the host takes this kernel only when n/4 and clean_n/4 stay below 2^31: 8.6 G
+    // elements): its loops compare, advance and branch on the index several times per float4, 64-bit integer arithmetic was
+    // its largest instruction class, and narrowing it took 128 x 10 s from 91.4 to 82.2 us; addresses are widened where
+    // they are formed.  l2 / snr keep 64-bit indices (one pointer increment per float4: 32-bit measured 2.8 % slower on l2).
+    typedef typename std::conditional<NORM == NORM_TV, unsigned, int64_t>::type idx_t;
+    const idx_t tid = (idx_t)blockIdx.x * kFT + threadIdx.x, nth = (idx_t)gridDim.x * kFT;
+    const idx_t n4 = (idx_t)(a.n >> 2);
+    const idx_t last4 = a.n > 0 ? (idx_t)((a.n - 1) >> 2) : 0;                    // i4 < last4  <=>  4 i4 + 4 < n
+    const idx_t lastc4 = a.clean_n > 0 ? (idx_t)((a.clean_n - 1) >> 2) : 0;
     float acc0 = 0.f, acc1 = 0.f;
     constexpr int RCN = ((STEP & 3) == PAA_STEP_ADAM) ? 2 : kRC;      // Adam carries 4 streams: fewer register-resident float4s
     float4 keep[RCN];
@@ -412,7 +427,7 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     // total variation: row-column of each thread's current float4, advanced without 64-bit division
     const int lane = threadIdx.x & 31;
     int colp = 0, stepp = 0;
-    if (NORM == NORM_TV) { colp = (int)((tid * 4) % a.T); stepp = (int)((nth * 4) % a.T); }
+    if (NORM == NORM_TV) { colp = (int)(((int64_t)tid * 4) % a.T); stepp = (int)(((int64_t)nth * 4) % a.T); }
 
     // tv: the clean audio rides the same loop as the perturbation -- float4 i4 of p, grad and clean are requested
     // together, so every thread keeps three independent streams in flight (93.6 us against 96.1 us at 128 x 10 s);
@@ -422,19 +437,19 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     // 14.3 us at (1,T) x 32 x 10 s); with one row per utterance riding costs registers and measured 2.4 % slower
     // (22.4 against 21.9 us), so that shape keeps the clean-only loop (RIDE = false).
     constexpr bool kRide = RIDE;
-    const int64_t c4 = (NORM == NORM_L2) ? 0 : (a.clean_n >> 2);
+    const idx_t c4 = (NORM == NORM_L2) ? 0 : (idx_t)(a.clean_n >> 2);
     const int Tc = a.clean_T;
     int colc = 0, stepc = 0;
-    if (NORM == NORM_TV) { colc = (int)((tid * 4) % Tc); stepc = (int)((nth * 4) % Tc); }
+    if (NORM == NORM_TV) { colc = (int)(((int64_t)tid * 4) % Tc); stepc = (int)(((int64_t)nth * 4) % Tc); }
 
     // clean part of one float4 (every lane of the warp calls it for tv: the element after the float4 comes from the
     // next lane by shuffle, only the last lane / the last float4 took it from memory in fetch)
-    auto clean_a = [&](const Raw4& raw, int64_t i4) {
+    auto clean_a = [&](const Raw4& raw, idx_t i4) {
         if (NORM == NORM_SNR) {
             if (i4 < c4) acc1 += (raw.c.x * raw.c.x + raw.c.y * raw.c.y) + (raw.c.z * raw.c.z + raw.c.w * raw.c.w);
         } else if (NORM == NORM_TV) {
             const bool act = i4 < c4;
-            const bool has_next = act && (i4 * 4 + 4 < a.clean_n);
+            const bool has_next = act && i4 < lastc4;
             float nx = __shfl_down_sync(0xffffffffu, raw.c.x, 1);
             if (has_next && (lane == 31 || i4 + 1 >= c4)) nx = raw.nc;
             if (act) acc1 += tv_quad(raw.c, nx, colc, Tc, has_next);
@@ -445,8 +460,8 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     // phase A on one float4 whose operands are already in registers: step, accumulate the norm, hand back the
     // stepped values.  For tv every lane of the warp calls it (act = in range): the element after the float4 comes
     // from the next lane by shuffle, only the last lane (or the last float4) recomputes it from memory.
-    auto phase_a = [&](const Raw4& raw, int64_t i4, bool act) -> float4 {
-        const int64_t i = i4 * 4;
+    auto phase_a = [&](const Raw4& raw, idx_t i4, bool act) -> float4 {
+        const int64_t i = (int64_t)i4 * 4;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (NORM != NORM_TV) {
             if (act) {
@@ -456,7 +471,7 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
         } else {
             if (act) x = finish4<STEP, false>(raw, i, s);
             float nx = __shfl_down_sync(0xffffffffu, x.x, 1);
-            const bool has_next = act && (i + 4 < a.n);
+            const bool has_next = act && i4 < last4;
             if (has_next && (lane == 31 || i4 + 1 >= n4)) {       // its operands came with the float4 (fetch)
                 float m1 = 0.f, v1 = 0.f;
                 nx = step_one<(STEP & 3) == PAA_STEP_ADAM ? PAA_STEP_NONE : (STEP & 3)>(raw.np, raw.ng, m1, v1, s);
@@ -468,22 +483,22 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
         if (kRide) clean_a(raw, i4);
         return x;
     };
-    auto fetch_clean = [&](Raw4& r, int64_t i4) {
+    auto fetch_clean = [&](Raw4& r, idx_t i4) {
         r.c = make_float4(0.f, 0.f, 0.f, 0.f);
         r.nc = 0.f;
         if (NORM != NORM_L2 && i4 < c4) {
-            r.c = ld4_stream(a.clean + i4 * 4);
-            if (NORM == NORM_TV && (lane == 31 || i4 + 1 >= c4) && i4 * 4 + 4 < a.clean_n) r.nc = a.clean[i4 * 4 + 4];
+            r.c = ld4_stream(a.clean + (int64_t)i4 * 4);
+            if (NORM == NORM_TV && (lane == 31 || i4 + 1 >= c4) && i4 < lastc4) r.nc = a.clean[(int64_t)i4 * 4 + 4];
         }
     };
-    auto fetch = [&](int64_t i4, bool act) -> Raw4 {
+    auto fetch = [&](idx_t i4, bool act) -> Raw4 {
         Raw4 r;
         r.p = r.g = r.m = r.v = make_float4(0.f, 0.f, 0.f, 0.f);
         r.np = r.ng = 0.f;
-        if (act) load_raw4<STEP>(r, a.p_in, i4 * 4, s);
-        if (NORM == NORM_TV && act && (lane == 31 || i4 + 1 >= n4) && i4 * 4 + 4 < a.n) {
-            r.np = a.p_in[i4 * 4 + 4];
-            if ((STEP & 3) != PAA_STEP_NONE) r.ng = ldg1<STEP>(s, i4 * 4 + 4);
+        if (act) load_raw4<STEP>(r, a.p_in, (int64_t)i4 * 4, s);
+        if (NORM == NORM_TV && act && (lane == 31 || i4 + 1 >= n4) && i4 < last4) {
+            r.np = a.p_in[(int64_t)i4 * 4 + 4];
+            if ((STEP & 3) != PAA_STEP_NONE) r.ng = ldg1<STEP>(s, (int64_t)i4 * 4 + 4);
         }
         if (kRide) fetch_clean(r, i4);
         return r;
@@ -499,25 +514,25 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
             for (int k = 0; k < G; ++k) raw[k] = fetch(tid + (k0 + k) * nth, tid + (k0 + k) * nth < n4);
 #pragma unroll
             for (int k = 0; k < G; ++k) {
-                const int64_t i4 = tid + (k0 + k) * nth;
+                const idx_t i4 = tid + (k0 + k) * nth;
                 const bool act = i4 < n4;
                 const float4 x = phase_a(raw[k], i4, act);
                 if (NORM == NORM_TV || act) keep[k0 + k] = x;
             }
         }
     }
-    int64_t i4 = tid + RCN * nth;
+    idx_t i4 = tid + RCN * nth;
     {   // the rest, software-pipelined two deep; (i4 - lane) is warp-uniform so whole warps stay for the shuffles
         int k = RCN;
         Raw4 cur = fetch(i4, i4 < n4);
         while (i4 - lane < n4) {
-            const int64_t i4n = i4 + nth;
+            const idx_t i4n = i4 + nth;
             const Raw4 nxt = fetch(i4n, i4n < n4);
             const bool act = i4 < n4;
             const float4 x = phase_a(cur, i4, act);
             if (act) {
                 if (k < RCN + sc_iters) cache[(k - RCN) * kFT + threadIdx.x] = x;
-                else if (a.write_q) st4(a.q_out + i4 * 4, x);
+                else if (a.write_q) st4(a.q_out + (int64_t)i4 * 4, x);
             }
             cur = nxt;
             i4 = i4n;
@@ -531,7 +546,7 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     }
     if (!kRide) i4 = tid;
     if (tid == 0) {                                         // the n % 4 trailing elements go through global memory
-        for (int64_t i = n4 << 2; i < a.n; ++i) {
+        for (int64_t i = (int64_t)n4 << 2; i < a.n; ++i) {
             const float x = stepped1<STEP, NORM != NORM_TV>(a.p_in, i, s);
             a.q_out[i] = x;
             if (NORM != NORM_TV) acc0 += x * x;
@@ -551,9 +566,9 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
             i4 += U * nth;
         }
         if (NORM == NORM_SNR) {
-            for (int64_t i = (c4 << 2) + tid; i < a.clean_n; i += nth) { const float c = a.clean[i]; acc1 += c * c; }
+            for (int64_t i = ((int64_t)c4 << 2) + tid; i < a.clean_n; i += nth) { const float c = a.clean[i]; acc1 += c * c; }
         } else {
-            for (int64_t i = (c4 << 2) + tid; i < a.clean_n; i += nth)
+            for (int64_t i = ((int64_t)c4 << 2) + tid; i < a.clean_n; i += nth)
                 if ((int)(i % Tc) != Tc - 1 && i + 1 < a.clean_n) acc1 += fabsf(a.clean[i + 1] - a.clean[i]);
         }
     }
@@ -590,18 +605,18 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     auto scaled = [sc](float4 x) { x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; return x; };
 #pragma unroll
     for (int k = 0; k < RCN; ++k) {
-        const int64_t i4 = tid + k * nth;
-        if (i4 < n4) st4(a.q_out + i4 * 4, scaled(keep[k]));
+        const idx_t i4 = tid + k * nth;
+        if (i4 < n4) st4(a.q_out + (int64_t)i4 * 4, scaled(keep[k]));
     }
     {
         int k = RCN;
-        for (int64_t i4 = tid + RCN * nth; i4 < n4; i4 += nth, ++k) {
-            if (k < RCN + sc_iters) st4(a.q_out + i4 * 4, scaled(cache[(k - RCN) * kFT + threadIdx.x]));
-            else if (sc != 1.f) st4(a.q_out + i4 * 4, scaled(ld4(a.q_out + i4 * 4)));
+        for (idx_t i4 = tid + RCN * nth; i4 < n4; i4 += nth, ++k) {
+            if (k < RCN + sc_iters) st4(a.q_out + (int64_t)i4 * 4, scaled(cache[(k - RCN) * kFT + threadIdx.x]));
+            else if (sc != 1.f) st4(a.q_out + (int64_t)i4 * 4, scaled(ld4(a.q_out + (int64_t)i4 * 4)));
         }
     }
     if (tid == 0 && sc != 1.f)
-        for (int64_t i = n4 << 2; i < a.n; ++i) a.q_out[i] *= sc;
+        for (int64_t i = (int64_t)n4 << 2; i < a.n; ++i) a.q_out[i] *= sc;
 }
 
 // ---- mode U helpers ------------------------------------------------------------------------------------------
@@ -901,7 +916,9 @@ int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int
         f.numel_from_stats = parts->clean_numel == 0;
         for (int k = 0; k < parts->n; ++k) f.cstat[k] = parts->clean_stats[k];
     }
-    if (vec && !h->no_coop) {
+    // k_fused indexes float4s with 32 bits (2^31 float4s = 8.6 G elements); beyond that the three-kernel form runs
+    const bool fits32 = (work >> 2) < ((int64_t)1 << 31) - ((int64_t)1 << 22);
+    if (vec && !h->no_coop && fits32) {
         // single cooperative launch; fall through to the three-kernel form only if the device refuses it
         void* kern = nullptr;
         int bps = 0;
