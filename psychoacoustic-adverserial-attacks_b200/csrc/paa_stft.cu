@@ -59,6 +59,7 @@ struct StftArgs {
     // per-bin op
     float bin_hz, f_min, f_max;
     int k_lo, k_hi;        // min_max_freqs as bin indices: keep k < k_lo or k >= k_hi
+    unsigned dead_slots;   // n_fft 1024, min_max_freqs: bit r set = every bin slot r of middle_paired touches is masked (r = 1..7)
     const float* spl_thresh;
     float ref_db;
     const float* scalars;  // OP_SCALE: scalars[PAA_S_SCALE]
@@ -460,6 +461,15 @@ __device__ __forceinline__ bool middle_paired(const StftArgs& a, cpx (&z)[2][8],
     }
 #pragma unroll
     for (int r = 1; r < 8; ++r) {
+        // min_max_freqs: a slot whose bins are masked in EVERY lane (kernel-uniform, worked out by the host: with the
+        // reference's default band 120 Hz .. 20 kHz only bins 0..7 survive, i.e. slots 1..7 are dead) contributes zeros
+        // to the inverse transform: no split, no merge.  (At least one slot is live, so a NaN / Inf frame still
+        // reaches every output sample through it, as torch's NaN * 0 does.)
+        if (OP == OP_MASK && SRC == SRC_TIME && SINK == SINK_TIME && ((a.dead_slots >> r) & 1)) {
+            z[0][r] = 0;
+            z[1][7 - r] = 0;
+            continue;
+        }
         // w = base * e^{i pi r / 8}
         const cpx bs = r < 4 ? base : baseB;
         const cpx w = fma2(rot90<+1>(bs), bcast(spi16(2 * r)), mul2(bs, bcast(cpi16(2 * r))));
@@ -1472,6 +1482,20 @@ void set_band(const paa_handle* h, StftArgs& a, double min_freq, double max_freq
     while (lo < h->F && (float)lo * h->bin_hz < a.f_min) ++lo;            // bins [0, lo) are below the band
     while (hi > 0 && (float)(hi - 1) * h->bin_hz > a.f_max) --hi;         // bins [hi, F) are above the band
     a.k_lo = lo; a.k_hi = hi;
+    // n_fft 1024: slots of the register-resident middle (middle_paired) whose bins are all masked.  Slot r >= 1 touches
+    // k = l + 64 r and 512 - k for the lanes l = 1..31, and in lane 0 the pairs (64 r, 512 - 64 r) for r = 1..3 and
+    // (64 r - 224, 736 - 64 r) for r = 4..7.  Slot 0 (DC, Nyquist, N/2 and the lowest bins) always runs.
+    a.dead_slots = 0;
+    if (h->n_fft == 1024) {
+        auto masked = [&](int k) { return k >= lo && k < hi; };
+        for (int r = 1; r < 8; ++r) {
+            bool dead = true;
+            for (int l = 1; l < 32 && dead; ++l) dead = masked(l + 64 * r) && masked(512 - (l + 64 * r));
+            const int k0 = r < 4 ? 64 * r : 64 * r - 224;
+            dead = dead && masked(k0) && masked(512 - k0);
+            if (dead) a.dead_slots |= 1u << r;
+        }
+    }
 }
 
 bool nola_check(const paa_handle* h, int n_frames);
