@@ -747,10 +747,10 @@ def transcript_identity(model, dev):
 
 
 def cpu_baseline(a):
-    sec = oracle_step_seconds(REF_SAMPLE, steps=1, warmup=1, rows=1 if a.universal else REF_SAMPLE)
+    sec = oracle_step_seconds(REF_SAMPLE, steps=3, warmup=1, rows=1 if a.universal else REF_SAMPLE)
     return {"value": round(REF_SAMPLE * SECONDS / sec, 3), "unit": "audio-s/s", "cores": torch.get_num_threads(),
             "kind": "port", "sample": f"oracle/paa_oracle.py attack_iteration (untargeted l2, PGD), batch {REF_SAMPLE} x {SECONDS} s "
-                                      f"(1/{TOTAL_BATCH // REF_SAMPLE} of the step's batch), 1 warm-up + 1 timed step"}
+                                      f"(1/{TOTAL_BATCH // REF_SAMPLE} of the step's batch), 1 warm-up + 3 timed steps"}
 
 
 def run_reference(a):
