@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
         Raw4 r;
         r.p = r.g = r.m = r.v = make_float4(0.f, 0.f, 0.f, 0.f);
         r.np = r.ng = 0.f;
-        if (act) load_raw4<STEP, NORM != NORM_L2 && (STEP & 3) != PAA_STEP_ADAM>(r, a.p_in, (int64_t)i4 * 4, s);
+        if (act) load_raw4<STEP, (STEP & 3) != PAA_STEP_ADAM>(r, a.p_in, (int64_t)i4 * 4, s);
         if (NORM == NORM_TV && act && (lane == 31 || i4 + 1 >= n4) && i4 < last4) {
             r.np = a.p_in[(int64_t)i4 * 4 + 4];
             if ((STEP & 3) != PAA_STEP_NONE) r.ng = ldg1<STEP>(s, (int64_t)i4 * 4 + 4);
@@ -614,9 +614,25 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
     }
     {
         int k = RCN;
-        for (idx_t i4 = tid + RCN * nth; i4 < n4; i4 += nth, ++k) {
-            if (k < RCN + sc_iters) st4(a.q_out + (int64_t)i4 * 4, scaled(cache[(k - RCN) * kFT + threadIdx.x]));
-            else if (sc != 1.f) st4(a.q_out + (int64_t)i4 * 4, scaled(ld4(a.q_out + (int64_t)i4 * 4)));
+        idx_t i4 = tid + RCN * nth;
+        for (; i4 < n4 && k < RCN + sc_iters; i4 += nth, ++k)
+            st4(a.q_out + (int64_t)i4 * 4, scaled(cache[(k - RCN) * kFT + threadIdx.x]));
+        // What did not fit on chip was written to q_out in phase A, in this order; it is revisited NEWEST FIRST: the most
+        // recently written ~100 MB are still in the 126 MB L2 (the inputs are streamed past it), and walking the same way
+        // again would evict every line just before it is needed (l2 512 x 10 s parks 280 MB).  Two float4 in flight.
+        if (sc != 1.f && i4 < n4) {
+            idx_t j = i4 + (idx_t)((n4 - 1 - i4) / nth) * nth;           // this thread's last float4
+            for (;;) {
+                const bool two = j >= i4 + nth;
+                const float4 x0 = ld4(a.q_out + (int64_t)j * 4);
+                float4 x1 = x0;
+                if (two) x1 = ld4(a.q_out + (int64_t)(j - nth) * 4);
+                st4(a.q_out + (int64_t)j * 4, scaled(x0));
+                if (!two) break;
+                st4(a.q_out + (int64_t)(j - nth) * 4, scaled(x1));
+                if (j < i4 + 2 * nth) break;
+                j -= 2 * nth;
+            }
         }
     }
     if (tid == 0 && sc != 1.f)
