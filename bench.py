@@ -62,10 +62,10 @@ FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4: CUDA-core fp32 FM
 WORKLOAD = ("configs[4]: untargeted l2 attack (PGD), batch 512 x 10 s @16 kHz in total, utterance-sharded, "
             "random-init wav2vec2-base")
 # `ncu --set full` of the dominant kernel at the N=1 workload (profiles/), bytes per launch; None until captured
-NCU_TRAFFIC_BYTES = 944_284_672 + 558_461_952
-NCU_TRAFFIC_SOURCE = ("profiles/r02d_ncu_full_k_fused_l2.txt: dram__bytes_read.sum + dram__bytes_write.sum of k_fused<l2,pgd> at "
-                      "512 x 10 s (944.3 + 558.5 MB; below the algorithmic 1638.4 MB because 12 M of the 82 M stepped elements "
-                      "stay in registers / shared memory across the grid barrier)")
+NCU_TRAFFIC_BYTES = 895_134_208 + 540_193_792
+NCU_TRAFFIC_SOURCE = ("profiles/r02i_ncu_full_k_fused_final.txt: dram__bytes_read.sum + dram__bytes_write.sum of k_fused<l2,pgd> at "
+                      "512 x 10 s (895.1 + 540.2 MB; below the algorithmic 1638.4 MB because 12 M of the 82 M stepped elements "
+                      "stay in registers / shared memory across the grid barrier and another ~12 M are re-read from L2)")
 
 
 def measured_peak():

@@ -411,7 +411,9 @@ constexpr int kFT = 512;
 constexpr int kRC = 4;
 constexpr int kSCMax = 12;
 
-template <int NORM, int STEP, bool RIDE>
+// PARKED: some of a thread's float4s do not fit registers + shared memory and wait in q_out (HBM / L2) between the phases.
+// The lean form (PARKED = false: every BASELINE shape up to 12 M elements, and all universal shapes) compiles that path out.
+template <int NORM, int STEP, bool RIDE, bool PARKED>
 __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, FinalArgs f, int sc_iters) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ float4 cache[];                       // [sc_iters][kFT]
@@ -535,7 +537,7 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
             const bool act = i4 < n4;
             const float4 x = phase_a(cur, i4, act);
             if (act) {
-                if (k < RCN + sc_iters) cache[(k - RCN) * kFT + threadIdx.x] = x;
+                if (!PARKED || k < RCN + sc_iters) cache[(k - RCN) * kFT + threadIdx.x] = x;
                 else if (a.write_q) st4(a.q_out + (int64_t)i4 * 4, x);
             }
             cur = nxt;
@@ -612,27 +614,28 @@ __global__ void __launch_bounds__(kFT, 2) k_fused(ReduceArgs a, StepDev s, Final
         const idx_t i4 = tid + k * nth;
         if (i4 < n4) st4(a.q_out + (int64_t)i4 * 4, scaled(keep[k]));
     }
-    {
+    // What did not fit on chip was written to q_out in phase A, in index order.  The PGD forms revisit it NEWEST FIRST:
+    // the most recently written part is still in the 126 MB L2 (the inputs are streamed past it), and walking the same way
+    // again would evict every line just before it is needed (l2 512 x 10 s parks 280 MB: 267.5 -> 253 us).  The Adam forms
+    // (four more streams through L2, nothing to gain) keep the single forward loop, and its register budget.
+    constexpr bool kNewestFirst = PARKED && (STEP & 3) != PAA_STEP_ADAM;
+    if (kNewestFirst) {
         int k = RCN;
         idx_t i4 = tid + RCN * nth;
         for (; i4 < n4 && k < RCN + sc_iters; i4 += nth, ++k)
             st4(a.q_out + (int64_t)i4 * 4, scaled(cache[(k - RCN) * kFT + threadIdx.x]));
-        // What did not fit on chip was written to q_out in phase A, in this order; it is revisited NEWEST FIRST: the most
-        // recently written ~100 MB are still in the 126 MB L2 (the inputs are streamed past it), and walking the same way
-        // again would evict every line just before it is needed (l2 512 x 10 s parks 280 MB).  Two float4 in flight.
         if (sc != 1.f && i4 < n4) {
             idx_t j = i4 + (idx_t)((n4 - 1 - i4) / nth) * nth;           // this thread's last float4
-            for (;;) {
-                const bool two = j >= i4 + nth;
-                const float4 x0 = ld4(a.q_out + (int64_t)j * 4);
-                float4 x1 = x0;
-                if (two) x1 = ld4(a.q_out + (int64_t)(j - nth) * 4);
-                st4(a.q_out + (int64_t)j * 4, scaled(x0));
-                if (!two) break;
-                st4(a.q_out + (int64_t)(j - nth) * 4, scaled(x1));
-                if (j < i4 + 2 * nth) break;
-                j -= 2 * nth;
+            for (;; j -= nth) {
+                st4(a.q_out + (int64_t)j * 4, scaled(ld4(a.q_out + (int64_t)j * 4)));
+                if (j == i4) break;
             }
+        }
+    } else {
+        int k = RCN;
+        for (idx_t i4 = tid + RCN * nth; i4 < n4; i4 += nth, ++k) {
+            if (!PARKED || k < RCN + sc_iters) st4(a.q_out + (int64_t)i4 * 4, scaled(cache[(k - RCN) * kFT + threadIdx.x]));
+            else if (sc != 1.f) st4(a.q_out + (int64_t)i4 * 4, scaled(ld4(a.q_out + (int64_t)i4 * 4)));
         }
     }
     if (tid == 0 && sc != 1.f)
@@ -859,10 +862,10 @@ int launch_reduce(paa_handle* h, const ReduceArgs& a, const StepDev& sd, int gri
 // The cooperative kernel of one (NORM, STEP, RIDE): its dynamic shared-memory ceiling is raised and its co-residency queried
 // once per device (not per call: small shapes are launch-latency bound), the answers cached per instantiation.
 constexpr int kMaxDevices = 64;
-template <int NORM, int STEP, bool RIDE>
+template <int NORM, int STEP, bool RIDE, bool PARKED>
 cudaError_t fused_kernel_r(const paa_handle* h, void** kern, int* blocks_per_sm) {
     static int cached[kMaxDevices];          // 0 = unknown, else 1 + blocks per SM
-    void* k = (void*)k_fused<NORM, STEP, RIDE>;
+    void* k = (void*)k_fused<NORM, STEP, RIDE, PARKED>;
     *kern = k;
     const int dev = h->device & (kMaxDevices - 1);
     int c = __atomic_load_n(&cached[dev], __ATOMIC_ACQUIRE);
@@ -880,11 +883,16 @@ cudaError_t fused_kernel_r(const paa_handle* h, void** kern, int* blocks_per_sm)
 }
 
 // tv always rides; snr when asked to (clean longer than the perturbation); l2 has no clean tensor
+template <int NORM, int STEP, bool PARKED>
+cudaError_t fused_kernel_p(const paa_handle* h, bool ride, void** kern, int* blocks_per_sm) {
+    if (NORM == NORM_TV) return fused_kernel_r<NORM, STEP, NORM == NORM_TV, PARKED>(h, kern, blocks_per_sm);
+    if (NORM == NORM_SNR && ride) return fused_kernel_r<NORM, STEP, NORM == NORM_SNR, PARKED>(h, kern, blocks_per_sm);
+    return fused_kernel_r<NORM, STEP, false, PARKED>(h, kern, blocks_per_sm);
+}
 template <int NORM, int STEP>
-cudaError_t fused_kernel(const paa_handle* h, bool ride, void** kern, int* blocks_per_sm) {
-    if (NORM == NORM_TV) return fused_kernel_r<NORM, STEP, NORM == NORM_TV>(h, kern, blocks_per_sm);
-    if (NORM == NORM_SNR && ride) return fused_kernel_r<NORM, STEP, NORM == NORM_SNR>(h, kern, blocks_per_sm);
-    return fused_kernel_r<NORM, STEP, false>(h, kern, blocks_per_sm);
+cudaError_t fused_kernel(const paa_handle* h, bool ride, bool parked, void** kern, int* blocks_per_sm) {
+    return parked ? fused_kernel_p<NORM, STEP, true>(h, ride, kern, blocks_per_sm)
+                  : fused_kernel_p<NORM, STEP, false>(h, ride, kern, blocks_per_sm);
 }
 
 template <int NORM>
@@ -944,13 +952,16 @@ int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int
         int bps = 0;
         cudaError_t e = cudaSuccess;
         const bool ride = a.clean_n > n;
-        switch (step_code(mode, sd)) {
-            case PAA_STEP_NONE: e = fused_kernel<NORM, PAA_STEP_NONE>(h, ride, &kern, &bps); break;
-            case PAA_STEP_PGD: e = fused_kernel<NORM, PAA_STEP_PGD>(h, ride, &kern, &bps); break;
-            case PAA_STEP_ADAM: e = fused_kernel<NORM, PAA_STEP_ADAM>(h, ride, &kern, &bps); break;
-            case PAA_STEP_PGD | kStepParts: e = fused_kernel<NORM, PAA_STEP_PGD | kStepParts>(h, ride, &kern, &bps); break;
-            default: e = fused_kernel<NORM, PAA_STEP_ADAM | kStepParts>(h, ride, &kern, &bps); break;
-        }
+        auto pick = [&](bool parked, void** k, int* b) {
+            switch (step_code(mode, sd)) {
+                case PAA_STEP_NONE: return fused_kernel<NORM, PAA_STEP_NONE>(h, ride, parked, k, b);
+                case PAA_STEP_PGD: return fused_kernel<NORM, PAA_STEP_PGD>(h, ride, parked, k, b);
+                case PAA_STEP_ADAM: return fused_kernel<NORM, PAA_STEP_ADAM>(h, ride, parked, k, b);
+                case PAA_STEP_PGD | kStepParts: return fused_kernel<NORM, PAA_STEP_PGD | kStepParts>(h, ride, parked, k, b);
+                default: return fused_kernel<NORM, PAA_STEP_ADAM | kStepParts>(h, ride, parked, k, b);
+            }
+        };
+        e = pick(true, &kern, &bps);
         if (e != cudaSuccess) return paa_cuda_fail(h, e);
         if (bps > 0) {
             const int max_grid = bps * h->num_sms;              // co-residency as the occupancy calculator reports it
@@ -958,6 +969,11 @@ int project_reduce(paa_handle* h, const float* p_in, float* p_out, int rows, int
             const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, (work4 + kFT - 1) / kFT));
             const int64_t iters = ((n >> 2) + (int64_t)grid * kFT - 1) / ((int64_t)grid * kFT);
             int sc_iters = (int)std::max<int64_t>(0, std::min<int64_t>(kSCMax, iters - (mode == PAA_STEP_ADAM ? 2 : kRC)));
+            if (mode != PAA_STEP_ADAM && iters <= kRC + kSCMax) {          // nothing parked in HBM: the lean form, if it is as resident
+                void* lean = nullptr;
+                int lbps = 0;
+                if (pick(false, &lean, &lbps) == cudaSuccess && lbps >= bps) kern = lean;
+            }
             size_t smem = (size_t)sc_iters * kFT * sizeof(float4);
             f.nblocks = grid;
             void* params[] = {(void*)&a, (void*)&sd, (void*)&f, (void*)&sc_iters};
